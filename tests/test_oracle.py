@@ -1,0 +1,95 @@
+"""CPU tests of the oracle itself (no GPU): the C port and, where present, the compiled
+reference must reproduce the committed golden vectors bit for bit; transpose and SpMV —
+for which the reference holds no code — are cross-checked against scipy.sparse."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import oracle
+
+VEC_OPS = ("columnSums", "colSums", "rowSums", "colMeans", "rowMeans")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+@pytest.fixture(scope="module")
+def port():
+    return oracle.Port()
+
+
+def test_vignette_known_answers(port):
+    """Known-answer test on the only literal matrix in the reference tree
+    (vignettes/Documentation.Rmd:213-216); expected values are SURVEY.md 8(c)'s."""
+    i = np.array([0, 2, 0, 1, 1], np.int32)
+    p = np.array([0, 0, 1, 2, 4, 5], np.int32)
+    x = np.array([0.41, 0.35, 0.84, 0.37, 0.26])
+    assert port.colSums(i, p, x, 5, 5).tolist() == [0.0, 0.41, 0.35, 1.21, 0.26]
+    assert port.columnSums(i, p, x, 5, 5).tolist() == [0.0, 0.41, 0.35, 1.21, 0.26]
+    assert port.rowSums(i, p, x, 5, 5).tolist() == [1.25, 0.63, 0.35, 0.0, 0.0]
+    assert port.colMeans(i, p, x, 5, 5).tolist() == [0.0, 0.08199999999999999, 0.069999999999999993,
+                                                       0.24199999999999999, 0.052000000000000005]
+    assert port.rowMeans(i, p, x, 5, 5).tolist() == [0.25, 0.126, 0.069999999999999993, 0.0, 0.0]
+    ti, tp, tx = port.transpose(i, p, x, 5, 5)
+    assert tp.tolist() == [0, 2, 4, 5, 5, 5] and ti.tolist() == [1, 3, 3, 4, 2]
+    assert tx.tolist() == [0.41, 0.84, 0.37, 0.26, 0.35]
+    v = np.arange(1.0, 6.0)
+    assert port.spmv(i, p, x, 5, 5, v).tolist() == [4.18, 2.7800000000000002, 1.0499999999999998, 0.0, 0.0]
+    assert port.spmv_t(i, p, x, 5, 5, v).tolist() == [0.0, 0.41, 1.0499999999999998, 1.58, 0.52]
+
+
+def test_port_matches_golden_bitwise(port, golden):
+    g = golden
+    for op in VEC_OPS:
+        got = getattr(port, op)(g["i"], g["p"], g["x"], g["nrow"], g["ncol"])
+        assert np.array_equal(bits(got), bits(g[op])), (g["name"], op)
+    ti, tp, tx = port.transpose(g["i"], g["p"], g["x"], g["nrow"], g["ncol"])
+    assert np.array_equal(ti, g["t_i"]) and np.array_equal(tp, g["t_p"])
+    assert np.array_equal(bits(tx), bits(g["t_x"]))
+    assert np.array_equal(bits(port.spmv(g["i"], g["p"], g["x"], g["nrow"], g["ncol"], g["v_col"])), bits(g["spmv"]))
+    assert np.array_equal(bits(port.spmv_t(g["i"], g["p"], g["x"], g["nrow"], g["ncol"], g["v_row"])),
+                          bits(g["spmv_t"]))
+
+
+@pytest.mark.skipif(not oracle.Ref.available(), reason="oracle/_ref not built (no /root/reference here)")
+def test_compiled_reference_matches_golden_bitwise(golden):
+    g = golden
+    ref = oracle.Ref()
+    for op in VEC_OPS:
+        got = getattr(ref, op)(g["i"], g["p"], g["x"], g["nrow"], g["ncol"])
+        assert np.array_equal(bits(got), bits(g[op])), (g["name"], op)
+    ti, tp, tx = ref.transpose(g["i"], g["p"], g["x"], g["nrow"], g["ncol"])
+    assert np.array_equal(ti, g["t_i"]) and np.array_equal(tp, g["t_p"]) and np.array_equal(bits(tx), bits(g["t_x"]))
+
+
+def test_transpose_and_spmv_agree_with_scipy(golden):
+    """The pieces the reference delegates (Matrix::t) or lacks (SpMV): independent cross-check."""
+    g = golden
+    nrow, ncol = g["nrow"], g["ncol"]
+    if nrow == 0 or ncol == 0:
+        pytest.skip("scipy rejects zero-sized index arrays inconsistently")
+    a = sp.csc_matrix((g["x"], g["i"], g["p"]), shape=(nrow, ncol))
+    r = a.tocsr()
+    r.sort_indices()
+    assert np.array_equal(r.indptr.astype(np.int32), g["t_p"])
+    assert np.array_equal(r.indices.astype(np.int32), g["t_i"])
+    assert np.array_equal(bits(r.data), bits(g["t_x"]))
+    if np.isfinite(g["x"]).all():
+        oracle.assert_within("spmv", a @ g["v_col"], g["spmv"], g["i"], g["p"], g["x"], nrow, ncol, g["v_col"])
+        oracle.assert_within("spmv_t", a.T @ g["v_row"], g["spmv_t"], g["i"], g["p"], g["x"], nrow, ncol, g["v_row"])
+        oracle.assert_within("rowSums", np.asarray(a.sum(axis=1)).ravel(), g["rowSums"], g["i"], g["p"], g["x"],
+                             nrow, ncol)
+        oracle.assert_within("colSums", np.asarray(a.sum(axis=0)).ravel(), g["colSums"], g["i"], g["p"], g["x"],
+                             nrow, ncol)
+
+
+def test_reference_bounds_check_is_an_error_not_ub():
+    """RcppSparse.h:142 indexes with Rcpp's checked operator(): a corrupt row index raises."""
+    if not oracle.Ref.available():
+        pytest.skip("oracle/_ref not built")
+    ref = oracle.Ref()
+    i = np.array([0, 9], np.int32)  # 9 >= nrow
+    p = np.array([0, 2], np.int32)
+    with pytest.raises(RuntimeError):
+        ref.rowSums(i, p, np.ones(2), 3, 1)
