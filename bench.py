@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py — the driver's benchmark contract for the RcppSparse hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own serial CPU code
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): 1,000,000 x 100,000 uniform
+rsparsematrix-style dgCMatrix, density 1e-3 (~1e8 stored entries, FP64 values, int32 indices),
+synthetic, generated straight into HBM by the integer-exact recipe of rcppsparse_b200/synth.py.
+One STEP = one pass of the four reductions the config names — colSums, rowSums, colMeans,
+rowMeans (reference RcppSparse.h:131-156) — over the device-resident matrix.
+`value` = stored entries swept per second over the whole job = ops * nnz / step time.
+
+At N > 1 (torchrun, one rank per GPU) every rank owns a C2-sized column block of a
+1M x (100k*N) matrix (weak scaling; columns are independent units), column results are
+all-gathered and row results all-reduced over NCCL inside the timed step.
+
+Extra keys beside the base contract: `per_op`, `roofline` (dominant kernel: the rowSums stream
+kernel, algorithmic bytes 12*nnz + 8*nrow per launch, timed live with CUDA events on the
+launching stream), `cpu_baseline` (reference code on a bounded column block, rank 0, N=1),
+`e2e` (same step through the host-buffer C ABI: upload of i/p/x from pinned memory + four
+results read back, every step), `clocks`, `gpu_launches`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OPS = ("colSums", "rowSums", "colMeans", "rowMeans")
+ABI_OP = {"colSums": "col_sums", "rowSums": "row_sums", "colMeans": "col_means", "rowMeans": "row_means",
+          "spmv": "spmv", "spmv_t": "spmv_t", "transpose": "transpose"}
+METRIC = "nnz/s"
+NOMINAL_HBM_GBS = 8000.0  # BASELINE.json metric: "% of 8 TB/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", help="C1|C2|C3|C4 (default C2 = BASELINE configs[1])")
+    ap.add_argument("--scale", type=float, default=1.0, help="column-count scale of the workload (tests)")
+    ap.add_argument("--ops", default=",".join(OPS), help="comma list; also spmv,spmv_t,transpose")
+    ap.add_argument("--cpu-cols", type=int, default=25000, help="columns of the block timed on the CPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def profile_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    try:
+        return json.load(open(path))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                                  ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# =====================================================================================================
+# reference arm: the reference's own serial CPU code (oracle/_ref when it was built from
+# /root/reference, else the C port of the same loops) on a bounded column block of the same workload
+# =====================================================================================================
+def cpu_block(spec, n_cols):
+    from rcppsparse_b200 import synth
+
+    n_cols = max(1, min(n_cols, spec.ncol))
+    i, p, x = synth.generate_host(spec, 0, n_cols)
+    return i, p, x, spec.nrow, n_cols
+
+
+def time_cpu(ops, block, reps):
+    """Best-of-reps wall time of each op on the block; returns (checker kind, {op: seconds}, nnz)."""
+    from oracle import oracle
+    from rcppsparse_b200 import synth
+
+    chk = oracle.best()
+    i, p, x, nrow, ncol = block
+    v_c, v_r = synth.dense_vector(1, ncol), synth.dense_vector(2, nrow)
+    out = {}
+    for op in ops:
+        best = float("inf")
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            if op == "spmv":
+                chk.spmv(i, p, x, nrow, ncol, v_c)
+            elif op == "spmv_t":
+                chk.spmv_t(i, p, x, nrow, ncol, v_r)
+            else:
+                getattr(chk, op)(i, p, x, nrow, ncol)
+            best = min(best, time.perf_counter() - t0)
+        out[op] = best
+    return chk.kind, out, int(x.shape[0])
+
+
+def run_reference(args, ops):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # other ranks exit 0 without work
+    from rcppsparse_b200 import synth
+
+    spec = synth.config(args.workload, args.scale)
+    block = cpu_block(spec, args.cpu_cols)
+    nnz = int(block[2].shape[0])
+    for _ in range(max(1, args.warmup // 3)):
+        time_cpu(ops, block, 1)
+    kind = "port"
+    step_s = []
+    for _ in range(args.steps):
+        kind, t, _ = time_cpu(ops, block, 1)
+        step_s.append(sum(t.values()))
+    step = float(np.median(step_s))
+    value = len(ops) * nnz / step
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "nnz/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(spec, args, ops, nnz_per_rank=None),
+        "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": 1, "kind": kind,
+                         "sample": f"columns [0,{block[4]}) of the workload ({nnz} stored entries), "
+                                   f"{len(ops)} ops per step, serial (the reference hot path has no parallel pragma)"},
+        "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(spec, args, ops, nnz_per_rank):
+    return {"workload": spec.name, "nrow": spec.nrow, "ncol_per_gpu": spec.ncol, "nnz_per_gpu": nnz_per_rank,
+            "ops_per_step": list(ops), "values": "f64", "indices": "int32", "seed": spec.seed,
+            "parallelism": f"column-sharded x{args.gpus}" if args.gpus > 1 else "single GPU",
+            "l2": "inputs (1.2 GB/rank at C2) exceed the 126 MB L2; no explicit flush"}
+
+
+# =====================================================================================================
+# this repo's arm
+# =====================================================================================================
+def run_b200(args, ops):
+    import torch
+    import torch.distributed as dist
+
+    from rcppsparse_b200 import DeviceMatrix, _lib, shard, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: bench.py measures the CUDA path and has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    spec = synth.config(args.workload, args.scale)
+    c0, c1 = rank * spec.ncol, (rank + 1) * spec.ncol  # weak scaling: every rank generates its own block
+    D = DeviceMatrix.synth(spec, c0, c1, device=local_rank)
+    nnz = D.nnz
+    local = shard.GpuLocal(D)  # binds the handle to torch's current stream
+    bounds = [k * spec.ncol for k in range(world + 1)]
+    S = shard.ShardedMatrix(local, bounds, rank, device=dev)
+    v_col = torch.empty(S.ncol, dtype=torch.float64, device=dev)
+    v_row = torch.empty(S.nrow, dtype=torch.float64, device=dev)
+    D.synth_vector_dev(spec.seed, 0, S.ncol, v_col)
+    D.synth_vector_dev(spec.seed + 7, 0, S.nrow, v_row)
+    T_keep = []
+
+    def run_op(op):
+        if op == "spmv":
+            return S.spmv(v_col)
+        if op == "spmv_t":
+            return S.spmv_t(v_row)
+        if op == "transpose":
+            T_keep.clear()
+            T_keep.append(D.transpose_dev())  # local block only (sharded transpose exchange: next round)
+            return None
+        return getattr(S, op)()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        for op in ops:
+            run_op(op)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib().sb200_launch_count()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(ops) + 1)] for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        ev[s][0].record()
+        for k, op in enumerate(ops):
+            run_op(op)
+            ev[s][k + 1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = _lib.lib().sb200_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_ms = ev[0][0].elapsed_time(ev[-1][-1])  # device time of exactly K steps on the launching stream
+    per_op_ms = {op: float(np.mean([ev[s][k].elapsed_time(ev[s][k + 1]) for s in range(args.steps)]))
+                 for k, op in enumerate(ops)}
+    per_op_min = {op: float(np.min([ev[s][k].elapsed_time(ev[s][k + 1]) for s in range(args.steps)]))
+                  for k, op in enumerate(ops)}
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    nnz_all = torch.tensor([nnz], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(nnz_all, op=dist.ReduceOp.SUM)
+    nnz_total = int(nnz_all.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    ms_per_step = total_ms / args.steps
+    value = len(ops) * nnz_total / (ms_per_step * 1e-3)
+    per_op = {}
+    for op in ops:
+        ab = D.algorithmic_bytes(ABI_OP[op])
+        gbs = ab / (per_op_ms[op] * 1e-3) / 1e9
+        per_op[op] = {"ms": per_op_ms[op], "ms_min": per_op_min[op], "nnz_per_s_per_gpu": nnz / (per_op_ms[op] * 1e-3),
+                      "algorithmic_bytes": ab, "achieved_GBps": gbs, "frac_of_measured": gbs / peak,
+                      "frac_of_nominal_8TBps": gbs / NOMINAL_HBM_GBS}
+    dom = max(ops, key=lambda o: per_op_ms[o])
+    dom_kernel = {"rowSums": "rowsum_stream_kernel", "rowMeans": "rowsum_stream_kernel", "colSums": "sweep_kernel<COLSUM>",
+                  "colMeans": "sweep_kernel<COLSUM>", "spmv": "sweep_kernel<SPMV>", "spmv_t": "sweep_kernel<SPMV_T>",
+                  "transpose": "transpose_band_kernel"}[dom]
+    roofline = {"bound": "hbm", "kernel": dom_kernel, "op": dom, "achieved": per_op[dom]["achieved_GBps"], "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": per_op[dom]["achieved_GBps"] / peak,
+                "frac_of_nominal_8TBps": per_op[dom]["achieved_GBps"] / NOMINAL_HBM_GBS,
+                "algorithmic_bytes_per_launch": per_op[dom]["algorithmic_bytes"], "ms_per_launch": per_op_ms[dom],
+                "timed": "CUDA events on the launching stream around the op (zero-fill + kernel), mean over the timed steps",
+                "traffic": profile_traffic()}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(spec, args, ops, nnz), "per_op": per_op, "roofline": roofline,
+        "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
+    }
+
+    # ---- e2e: the host-buffer C ABI, upload + results every step (N = 1 only) -------------------------------
+    if world == 1 and not args.no_e2e:
+        try:
+            line["e2e"] = measure_e2e(args, ops, D, nnz, local_rank)
+        except Exception as e:  # never lose the device-resident line
+            line["e2e"] = {"value": None, "unit": "nnz/s", "error": f"{type(e).__name__}: {e}"}
+    elif world > 1:
+        line["e2e"] = {"value": None, "unit": "nnz/s", "note": "measured at N=1 (host-buffer C ABI is per process)"}
+
+    # ---- cpu_baseline: the reference's serial code on a bounded block, rank 0, N = 1 only ------------------------
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            block = cpu_block(spec, args.cpu_cols)
+            kind, t_cpu, nnz_cpu = time_cpu(ops, block, 3)
+            cpu_step = sum(t_cpu.values())
+            line["cpu_baseline"] = {
+                "value": len(ops) * nnz_cpu / cpu_step, "unit": "nnz/s", "cores": 1, "kind": kind,
+                "host_cores_available": os.cpu_count(),
+                "sample": f"columns [0,{block[4]}) of the workload ({nnz_cpu} stored entries), best of 3 per op, serial",
+                "per_op_nnz_per_s": {op: nnz_cpu / t_cpu[op] for op in ops}}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "nnz/s", "error": f"{type(e).__name__}: {e}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_e2e(args, ops, D, nnz, device):
+    """Same step through the reference-facing host-buffer entry points: every step uploads i/p/x from
+    pinned host memory into a fresh mirror (what one .Call from R pays), runs the ops, and reads every
+    result vector back to host."""
+    import torch
+
+    from rcppsparse_b200 import DeviceMatrix
+
+    i, p, x = D.download_columns()
+    hi = torch.from_numpy(i).pin_memory()
+    hp = torch.from_numpy(p).pin_memory()
+    hx = torch.from_numpy(x).pin_memory()
+    del i, p, x
+    v_c = np.ones(D.ncol)
+    v_r = np.ones(D.nrow)
+    host_fn = {"colSums": "col_sums", "rowSums": "row_sums", "colMeans": "col_means", "rowMeans": "row_means"}
+
+    def step():
+        with DeviceMatrix.from_host(hi, hp, hx, D.nrow, D.ncol, device=device, validate=True) as M:
+            outs = []
+            for op in ops:
+                if op in host_fn:
+                    outs.append(getattr(M, host_fn[op])())
+                elif op == "spmv":
+                    outs.append(M.spmv(v_c))
+                elif op == "spmv_t":
+                    outs.append(M.spmv_t(v_r))
+                elif op == "transpose":
+                    outs.append(M.transpose_host()[1])
+            return outs
+
+    step()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(args.e2e_steps):
+        t0 = time.perf_counter()
+        step()
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    dt = float(np.median(times))
+    h2d = 12 * nnz + 4 * (D.ncol + 1)
+    d2h = sum(8 * (D.ncol if op in ("colSums", "colMeans", "spmv_t") else D.nrow) for op in ops if op != "transpose")
+    return {"value": len(ops) * nnz / dt, "unit": "nnz/s", "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+            "what": "sb200_matrix_create (pinned-host upload + validation + plan) + host-buffer ops + destroy, wall clock"}
+
+
+def main():
+    args = parse_args()
+    ops = tuple(o for o in args.ops.split(",") if o)
+    for o in ops:
+        if o not in ABI_OP:
+            raise SystemExit(f"unknown op {o}")
+    if args.impl == "reference":
+        run_reference(args, tuple(o for o in ops if o != "transpose") or OPS)
+    else:
+        run_b200(args, ops)
+
+
+if __name__ == "__main__":
+    main()

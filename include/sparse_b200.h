@@ -1,0 +1,140 @@
+/* sparse_b200.h — C ABI of libsparse_b200: the B200 (sm_100a) backend for the
+ * column-sweep hot path of zdebruine/RcppSparse.
+ *
+ * Plain C, plain pointers and sizes, no exceptions, no torch/Rcpp types.  Every entry
+ * point returns an int status (0 = SB200_OK, negative = category below); the message for
+ * the calling thread's last failure is sb200_last_error().  The library never calls the R
+ * API and never longjmps, so it is safe under BEGIN_RCPP/END_RCPP (reference
+ * src/RcppExports.cpp:17,23): the C++ header turns a non-zero status into an exception.
+ *
+ * "reference" below = /root/reference (zdebruine/RcppSparse); RcppSparse.h =
+ * inst/include/RcppSparse.h.  Layout everywhere is the dgCMatrix slot layout of
+ * RcppSparse.h:29-30: x double[nnz], i int32[nnz] (0-based rows, strictly ascending inside
+ * a column), p int32[ncol+1] (p[0]=0, p[ncol]=nnz), Dim = (nrow, ncol).
+ *
+ * There is NO CPU fallback: without a CUDA device every compute entry returns
+ * SB200_E_NODEVICE.
+ */
+#ifndef SPARSE_B200_H
+#define SPARSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_ABI_VERSION 1
+
+/* status codes */
+#define SB200_OK 0
+#define SB200_E_INVALID (-1)   /* bad argument (null pointer, negative size, wrong handle) */
+#define SB200_E_CUDA (-2)      /* a CUDA runtime call or kernel failed; message has the CUDA text */
+#define SB200_E_NOMEM (-3)     /* device or host allocation failed */
+#define SB200_E_STRUCTURE (-4) /* i/p violate the dgCMatrix invariants (what the reference turns into
+                                  Rcpp::index_out_of_bounds at RcppSparse.h:135,142, or silent UB) */
+#define SB200_E_NODEVICE (-5)  /* no CUDA device / requested device absent */
+#define SB200_E_UNSUPPORTED (-6)
+
+/* flags for sb200_matrix_create* */
+#define SB200_PIN_HOST 1u    /* cudaHostRegister i/p/x for the upload (R-owned memory), unregister after */
+#define SB200_NO_VALIDATE 2u /* skip the structure-validation kernel (trusted producer, benchmarks) */
+
+/* Opaque device-resident mirror of one dgCMatrix (or of one column block of it, which is
+ * itself a valid dgCMatrix with the same nrow — the unit of multi-GPU sharding).
+ * Replaces the four Rcpp handles of RcppSparse.h:29-30 as the thing kernels read. */
+typedef struct sb200_matrix sb200_matrix;
+
+/* ---- library / errors ------------------------------------------------------------------ */
+int sb200_abi_version(void);
+const char* sb200_last_error(void);      /* thread-local, never NULL */
+int sb200_device_count(int* count);      /* SB200_E_NODEVICE when there is none */
+
+/* ---- mirror lifecycle -------------------------------------------------------------------
+ * sb200_matrix_create: what Exporter::get() / the 4-vector constructor do in the reference
+ * (RcppSparse.h:33,417-419) plus the one-time upload.  The host arrays are BORROWED for the
+ * duration of the call only (copied to HBM); they may be R-owned (use SB200_PIN_HOST) or
+ * already pinned.  Structure is validated on the device unless SB200_NO_VALIDATE. */
+int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int32_t nrow, int32_t ncol,
+                        int64_t nnz, int device, unsigned flags, sb200_matrix** out);
+/* Adopt arrays that already live in HBM on `device` (a generator's output, a torch tensor,
+ * a rank's column shard).  Not copied, not freed by destroy; must outlive the handle.
+ * d_i and d_x must be 16-byte aligned and readable up to the next 16-byte boundary past
+ * their last element; d_p likewise (cudaMalloc / torch allocations satisfy this). */
+int sb200_matrix_adopt_device(const int32_t* d_i, const int32_t* d_p, const double* d_x, int32_t nrow,
+                              int32_t ncol, int64_t nnz, int device, unsigned flags, sb200_matrix** out);
+int sb200_matrix_destroy(sb200_matrix* m);
+int sb200_matrix_dims(const sb200_matrix* m, int32_t* nrow, int32_t* ncol, int64_t* nnz);
+/* The view aliases R memory and users may mutate x in place (reference
+ * vignettes/Documentation.Rmd:325-347); this re-uploads x[nnz] into the mirror. */
+int sb200_matrix_refresh_values(sb200_matrix* m, const double* x);
+/* Run this handle's work on a caller-owned CUDA stream (a cudaStream_t passed as void*,
+ * e.g. torch.cuda.current_stream().cuda_stream) so the caller's events bracket it. */
+int sb200_matrix_set_stream(sb200_matrix* m, void* cuda_stream);
+int sb200_matrix_sync(sb200_matrix* m);
+/* Device pointers of the mirror (for callers that shard or inspect it). */
+int sb200_matrix_device_arrays(const sb200_matrix* m, const int32_t** d_i, const int32_t** d_p,
+                               const double** d_x);
+
+/* ---- the sweeps, host-buffer form (what the C++ header calls) -----------------------------
+ * Output buffers are caller-allocated host memory of the stated length (the NumericVector
+ * the header allocates); the call returns after the result is in `out`.
+ *   sb200_col_sums   replaces Matrix::colSums()  RcppSparse.h:131-137 and columnSums() src/example.cpp:26-32
+ *   sb200_row_sums   replaces Matrix::rowSums()  RcppSparse.h:138-144
+ *   sb200_col_means  replaces Matrix::colMeans() RcppSparse.h:145-150 (sum / nrow, true division)
+ *   sb200_row_means  replaces Matrix::rowMeans() RcppSparse.h:151-156 (sum / ncol)
+ *   sb200_spmv       y[nrow] = A v[ncol]   — the InnerIterator sweep y[it.row()] += it.value()*v[col]
+ *   sb200_spmv_t     y[ncol] = A^T v[nrow] — the sweep y[col] += it.value()*v[it.row()]
+ *                    (idiom of src/example.cpp:28-30; the reference has no SpMV function)
+ *   sb200_transpose  replaces Matrix::transpose() RcppSparse.h:375-385: canonical CSC of A^T,
+ *                    p_out[nrow+1], i_out[nnz] ascending inside each new column, x_out[nnz] */
+int sb200_col_sums(sb200_matrix* m, double* out /* ncol */);
+int sb200_row_sums(sb200_matrix* m, double* out /* nrow */);
+int sb200_col_means(sb200_matrix* m, double* out /* ncol */);
+int sb200_row_means(sb200_matrix* m, double* out /* nrow */);
+int sb200_spmv(sb200_matrix* m, const double* v /* ncol */, double* y /* nrow */);
+int sb200_spmv_t(sb200_matrix* m, const double* v /* nrow */, double* y /* ncol */);
+int sb200_transpose(sb200_matrix* m, int32_t* p_out, int32_t* i_out, double* x_out);
+
+/* ---- the sweeps, device-buffer form (asynchronous on the handle's stream) ------------------
+ * Operands and results are device pointers on the handle's device.  Used by the sharding
+ * layer (results feed NCCL collectives without touching the host) and by bench.py.
+ * `divisor` of the *_scaled forms: result = sum / divisor (0 = no scaling); a sharded
+ * rowMeans/colMeans passes the GLOBAL dimension here. */
+int sb200_col_sums_dev(sb200_matrix* m, double divisor, double* d_out /* ncol */);
+int sb200_row_sums_dev(sb200_matrix* m, double divisor, double* d_out /* nrow */);
+int sb200_spmv_dev(sb200_matrix* m, const double* d_v /* ncol */, double* d_y /* nrow */);
+int sb200_spmv_t_dev(sb200_matrix* m, const double* d_v /* nrow */, double* d_y /* ncol */);
+/* Result stays in HBM as a new handle that owns its arrays (Dim swapped). */
+int sb200_transpose_dev(sb200_matrix* m, sb200_matrix** out);
+/* d[k] /= divisor for k < n, on the handle's stream (mean scaling after a cross-rank reduce). */
+int sb200_vec_div_dev(sb200_matrix* m, double* d, int64_t n, double divisor);
+
+/* ---- introspection for benchmarks ----------------------------------------------------------
+ * Number of kernel launches this library has issued in this process (all handles). */
+int64_t sb200_launch_count(void);
+/* Name and per-launch algorithmic bytes (SURVEY.md 8d figures) of the dominant kernel of an op:
+ * op = "col_sums" | "row_sums" | "col_means" | "row_means" | "spmv" | "spmv_t" | "transpose". */
+int sb200_algorithmic_bytes(const sb200_matrix* m, const char* op, int64_t* bytes);
+
+/* ---- synthetic matrices generated straight into HBM (tests and benchmarks) -----------------
+ * Integer-exact recipe shared with rcppsparse_b200/synth.py (bit-identical output).
+ * len_table: int64[4097] quantile table; bands: K ascending row bands [lo,hi) with weights.
+ * Columns [col_begin, col_end) are generated; p is rebased to 0.  The new handle owns its arrays. */
+int sb200_synth_create(int32_t nrow, int64_t col_begin, int64_t col_end, uint64_t seed,
+                       const int64_t* len_table, int32_t empty_permille, int32_t n_bands,
+                       const int64_t* band_lo, const int64_t* band_hi, const int64_t* band_w, int device,
+                       sb200_matrix** out);
+/* v[k] for k in [begin, begin+n): the dense SpMV operand of the recipe (seed+1 stream). */
+int sb200_synth_vector_dev(sb200_matrix* m, uint64_t seed, int64_t begin, int64_t n, double* d_out);
+/* Copy a column block [c0, c1) of the mirror back to host buffers (p rebased to 0);
+ * sizes: p_out[c1-c0+1]; i_out/x_out sized by the block's nnz (query with i_out = NULL:
+ * only *nnz_out is written). */
+int sb200_matrix_download_columns(sb200_matrix* m, int64_t c0, int64_t c1, int32_t* i_out, int32_t* p_out,
+                                  double* x_out, int64_t* nnz_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARSE_B200_H */

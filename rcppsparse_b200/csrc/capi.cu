@@ -1,0 +1,419 @@
+// extern "C" surface of libsparse_b200 (declared in include/sparse_b200.h) and the mirror's lifecycle.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+#include <string>
+
+#include "common.cuh"
+
+namespace sb200 {
+
+static thread_local std::string t_last_error;
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string& msg) { t_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  t_last_error = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  const char* base = strrchr(file, '/');
+  t_last_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + (base ? base + 1 : file) +
+                 ":" + std::to_string(line) + " (" + what + ")";
+  if (e == cudaErrorMemoryAllocation) return SB200_E_NOMEM;
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return SB200_E_NODEVICE;
+  return SB200_E_CUDA;
+}
+
+size_t padded_bytes(size_t bytes) { return ((bytes + 15) / 16) * 16 + 16; }
+
+static int require_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(SB200_E_NODEVICE, "no CUDA device available: libsparse_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= n) return fail(SB200_E_NODEVICE, "requested CUDA device " + std::to_string(device) + " not present");
+  return SB200_OK;
+}
+
+static void free_matrix(sb200_matrix* m) {
+  if (!m) return;
+  if (m->owns_arrays) {
+    cudaFree(m->d_i);
+    cudaFree(m->d_p);
+    cudaFree(m->d_x);
+  }
+  cudaFree(m->d_plan);
+  cudaFree(m->d_ws);
+  cudaFree(m->d_stage_in);
+  cudaFree(m->d_stage_out);
+  if (m->owns_stream && m->stream) cudaStreamDestroy(m->stream);
+  m->magic = 0;
+  delete m;
+}
+
+static int new_handle(int device, int32_t nrow, int32_t ncol, int64_t nnz, sb200_matrix** out) {
+  if (nrow < 0 || ncol < 0 || nnz < 0) return fail(SB200_E_INVALID, "negative dimension");
+  if (nnz > 2147483647LL) return fail(SB200_E_INVALID, "nnz exceeds int32: dgCMatrix p/i are int32 (reference RcppSparse.h:30)");
+  SB_TRY(require_device(device));
+  sb200_matrix* m = new (std::nothrow) sb200_matrix();
+  if (!m) return fail(SB200_E_NOMEM, "host allocation failed");
+  memset(m, 0, sizeof(*m));
+  m->magic = MATRIX_MAGIC;
+  m->device = device;
+  m->nrow = nrow;
+  m->ncol = ncol;
+  m->nnz = nnz;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    free_matrix(m);
+    return cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__);
+  }
+  m->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    free_matrix(m);
+    return cuda_fail(e, "cudaStreamCreateWithFlags", __FILE__, __LINE__);
+  }
+  m->owns_stream = true;
+  *out = m;
+  return SB200_OK;
+}
+
+int alloc_matrix(int device, int32_t nrow, int32_t ncol, int64_t nnz, sb200_matrix** out) {
+  sb200_matrix* m = nullptr;
+  SB_TRY(new_handle(device, nrow, ncol, nnz, &m));
+  m->owns_arrays = true;
+  cudaError_t e = cudaMalloc(&m->d_i, padded_bytes(sizeof(int32_t) * static_cast<size_t>(nnz)));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_p, padded_bytes(sizeof(int32_t) * (static_cast<size_t>(ncol) + 1)));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_x, padded_bytes(sizeof(double) * static_cast<size_t>(nnz)));
+  if (e != cudaSuccess) {
+    free_matrix(m);
+    return cuda_fail(e, "cudaMalloc(mirror arrays)", __FILE__, __LINE__);
+  }
+  *out = m;
+  return SB200_OK;
+}
+
+int finish_matrix(sb200_matrix* m, unsigned flags) {
+  m->ws_bytes = 16 + 4 * 1024 + 8 * 1024 + 64;
+  SB_CUDA(cudaMalloc(&m->d_ws, m->ws_bytes));
+  SB_CUDA(cudaMemsetAsync(m->d_ws, 0, m->ws_bytes, m->stream));
+  m->stage_len = (m->nrow > m->ncol ? m->nrow : m->ncol);
+  if (m->stage_len < 1) m->stage_len = 1;
+  SB_CUDA(cudaMalloc(&m->d_stage_in, padded_bytes(sizeof(double) * static_cast<size_t>(m->stage_len))));
+  SB_CUDA(cudaMalloc(&m->d_stage_out, padded_bytes(sizeof(double) * static_cast<size_t>(m->stage_len))));
+  if (!(flags & SB200_NO_VALIDATE)) SB_TRY(validate_structure(m));
+  SB_TRY(build_sweep_plan(m));
+  SB_CUDA(cudaStreamSynchronize(m->stream));
+  return SB200_OK;
+}
+
+}  // namespace sb200
+
+using namespace sb200;
+
+#define ENTER(m)                        \
+  SB_TRY(check_handle(m));              \
+  DeviceGuard guard_((m)->device);      \
+  if (!guard_.ok) return fail(SB200_E_CUDA, "cudaSetDevice failed")
+
+extern "C" {
+
+int sb200_abi_version(void) { return SB200_ABI_VERSION; }
+const char* sb200_last_error(void) { return t_last_error.c_str(); }
+
+int sb200_device_count(int* count) {
+  if (!count) return fail(SB200_E_INVALID, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    *count = 0;
+    return fail(SB200_E_NODEVICE, "no CUDA device available");
+  }
+  *count = n;
+  return SB200_OK;
+}
+
+int64_t sb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int32_t nrow, int32_t ncol, int64_t nnz,
+                        int device, unsigned flags, sb200_matrix** out) {
+  if (!out) return fail(SB200_E_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!p || (nnz > 0 && (!i || !x))) return fail(SB200_E_INVALID, "NULL slot array");
+  SB_TRY(require_device(device));
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(SB200_E_CUDA, "cudaSetDevice failed");
+  sb200_matrix* m = nullptr;
+  SB_TRY(alloc_matrix(device, nrow, ncol, nnz, &m));
+  const size_t bi = sizeof(int32_t) * static_cast<size_t>(nnz), bp = sizeof(int32_t) * (static_cast<size_t>(ncol) + 1),
+               bx = sizeof(double) * static_cast<size_t>(nnz);
+  bool pinned_i = false, pinned_x = false;
+  if ((flags & SB200_PIN_HOST) && nnz > 0) {
+    // R owns these pages; pinning the enclosing pages lets the copy engine stream them directly
+    pinned_i = cudaHostRegister(const_cast<int32_t*>(i), bi, cudaHostRegisterReadOnly) == cudaSuccess;
+    if (!pinned_i) pinned_i = cudaHostRegister(const_cast<int32_t*>(i), bi, cudaHostRegisterDefault) == cudaSuccess;
+    pinned_x = cudaHostRegister(const_cast<double*>(x), bx, cudaHostRegisterReadOnly) == cudaSuccess;
+    if (!pinned_x) pinned_x = cudaHostRegister(const_cast<double*>(x), bx, cudaHostRegisterDefault) == cudaSuccess;
+    cudaGetLastError();
+  }
+  cudaError_t e = cudaMemcpyAsync(m->d_p, p, bp, cudaMemcpyHostToDevice, m->stream);
+  if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(m->d_i, i, bi, cudaMemcpyHostToDevice, m->stream);
+  if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(m->d_x, x, bx, cudaMemcpyHostToDevice, m->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+  if (pinned_i) cudaHostUnregister(const_cast<int32_t*>(i));
+  if (pinned_x) cudaHostUnregister(const_cast<double*>(x));
+  if (e != cudaSuccess) {
+    free_matrix(m);
+    return cuda_fail(e, "upload of i/p/x", __FILE__, __LINE__);
+  }
+  const int rc = finish_matrix(m, flags);
+  if (rc != SB200_OK) {
+    free_matrix(m);
+    return rc;
+  }
+  *out = m;
+  return SB200_OK;
+}
+
+int sb200_matrix_adopt_device(const int32_t* d_i, const int32_t* d_p, const double* d_x, int32_t nrow, int32_t ncol,
+                              int64_t nnz, int device, unsigned flags, sb200_matrix** out) {
+  if (!out) return fail(SB200_E_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!d_p || (nnz > 0 && (!d_i || !d_x))) return fail(SB200_E_INVALID, "NULL device array");
+  if ((reinterpret_cast<uintptr_t>(d_i) | reinterpret_cast<uintptr_t>(d_p) | reinterpret_cast<uintptr_t>(d_x)) & 15)
+    return fail(SB200_E_INVALID, "device arrays must be 16-byte aligned");
+  SB_TRY(require_device(device));
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(SB200_E_CUDA, "cudaSetDevice failed");
+  sb200_matrix* m = nullptr;
+  SB_TRY(new_handle(device, nrow, ncol, nnz, &m));
+  m->owns_arrays = false;
+  m->d_i = const_cast<int32_t*>(d_i);
+  m->d_p = const_cast<int32_t*>(d_p);
+  m->d_x = const_cast<double*>(d_x);
+  const int rc = finish_matrix(m, flags);
+  if (rc != SB200_OK) {
+    free_matrix(m);
+    return rc;
+  }
+  *out = m;
+  return SB200_OK;
+}
+
+int sb200_matrix_destroy(sb200_matrix* m) {
+  if (!m) return SB200_OK;
+  SB_TRY(check_handle(m));
+  DeviceGuard guard(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  free_matrix(m);
+  return SB200_OK;
+}
+
+int sb200_matrix_dims(const sb200_matrix* m, int32_t* nrow, int32_t* ncol, int64_t* nnz) {
+  SB_TRY(check_handle(m));
+  if (nrow) *nrow = m->nrow;
+  if (ncol) *ncol = m->ncol;
+  if (nnz) *nnz = m->nnz;
+  return SB200_OK;
+}
+
+int sb200_matrix_refresh_values(sb200_matrix* m, const double* x) {
+  ENTER(m);
+  if (m->nnz == 0) return SB200_OK;
+  if (!x) return fail(SB200_E_INVALID, "x is NULL");
+  SB_CUDA(cudaMemcpyAsync(m->d_x, x, sizeof(double) * static_cast<size_t>(m->nnz), cudaMemcpyHostToDevice, m->stream));
+  SB_CUDA(cudaStreamSynchronize(m->stream));
+  return SB200_OK;
+}
+
+int sb200_matrix_set_stream(sb200_matrix* m, void* cuda_stream) {
+  ENTER(m);
+  SB_CUDA(cudaStreamSynchronize(m->stream));
+  if (m->owns_stream && m->stream) cudaStreamDestroy(m->stream);
+  m->stream = static_cast<cudaStream_t>(cuda_stream);
+  m->owns_stream = false;
+  return SB200_OK;
+}
+
+int sb200_matrix_sync(sb200_matrix* m) {
+  ENTER(m);
+  SB_CUDA(cudaStreamSynchronize(m->stream));
+  return SB200_OK;
+}
+
+int sb200_matrix_device_arrays(const sb200_matrix* m, const int32_t** d_i, const int32_t** d_p, const double** d_x) {
+  SB_TRY(check_handle(m));
+  if (d_i) *d_i = m->d_i;
+  if (d_p) *d_p = m->d_p;
+  if (d_x) *d_x = m->d_x;
+  return SB200_OK;
+}
+
+// ---- device-buffer form ---------------------------------------------------------------------------------
+int sb200_col_sums_dev(sb200_matrix* m, double divisor, double* d_out) {
+  ENTER(m);
+  if (m->ncol > 0 && !d_out) return fail(SB200_E_INVALID, "d_out is NULL");
+  return launch_sweep(m, SWEEP_COLSUM, nullptr, divisor, d_out);
+}
+int sb200_row_sums_dev(sb200_matrix* m, double divisor, double* d_out) {
+  ENTER(m);
+  if (m->nrow > 0 && !d_out) return fail(SB200_E_INVALID, "d_out is NULL");
+  return launch_sweep(m, SWEEP_ROWSUM, nullptr, divisor, d_out);
+}
+int sb200_spmv_dev(sb200_matrix* m, const double* d_v, double* d_y) {
+  ENTER(m);
+  if ((m->ncol > 0 && !d_v) || (m->nrow > 0 && !d_y)) return fail(SB200_E_INVALID, "NULL operand");
+  return launch_sweep(m, SWEEP_SPMV, d_v, 0.0, d_y);
+}
+int sb200_spmv_t_dev(sb200_matrix* m, const double* d_v, double* d_y) {
+  ENTER(m);
+  if ((m->nrow > 0 && !d_v) || (m->ncol > 0 && !d_y)) return fail(SB200_E_INVALID, "NULL operand");
+  return launch_sweep(m, SWEEP_SPMV_T, d_v, 0.0, d_y);
+}
+int sb200_vec_div_dev(sb200_matrix* m, double* d, int64_t n, double divisor) {
+  ENTER(m);
+  return launch_vec_div(m->stream, d, n, divisor);
+}
+
+int sb200_transpose_dev(sb200_matrix* m, sb200_matrix** out) {
+  if (!out) return fail(SB200_E_INVALID, "out is NULL");
+  *out = nullptr;
+  ENTER(m);
+  sb200_matrix* t = nullptr;
+  SB_TRY(alloc_matrix(m->device, m->ncol, m->nrow, m->nnz, &t));
+  int rc = transpose_device(m, t->d_p, t->d_i, t->d_x);
+  if (rc == SB200_OK) rc = cudaStreamSynchronize(m->stream) == cudaSuccess ? SB200_OK : fail(SB200_E_CUDA, "transpose: stream sync failed");
+  // the result is canonical by construction; skip re-validation
+  if (rc == SB200_OK) rc = finish_matrix(t, SB200_NO_VALIDATE);
+  if (rc != SB200_OK) {
+    free_matrix(t);
+    return rc;
+  }
+  *out = t;
+  return SB200_OK;
+}
+
+// ---- host-buffer form: stage through the handle's device buffers ---------------------------------------------
+static int run_to_host(sb200_matrix* m, SweepMode mode, const double* v_host, int64_t v_len, double divisor,
+                       double* out_host, int64_t out_len) {
+  if (out_len > 0 && !out_host) return fail(SB200_E_INVALID, "output buffer is NULL");
+  if (v_len > 0) {
+    if (!v_host) return fail(SB200_E_INVALID, "operand vector is NULL");
+    SB_CUDA(cudaMemcpyAsync(m->d_stage_in, v_host, sizeof(double) * static_cast<size_t>(v_len), cudaMemcpyHostToDevice,
+                            m->stream));
+  }
+  SB_TRY(launch_sweep(m, mode, m->d_stage_in, divisor, m->d_stage_out));
+  if (out_len > 0)
+    SB_CUDA(cudaMemcpyAsync(out_host, m->d_stage_out, sizeof(double) * static_cast<size_t>(out_len),
+                            cudaMemcpyDeviceToHost, m->stream));
+  SB_CUDA(cudaStreamSynchronize(m->stream));
+  return SB200_OK;
+}
+
+int sb200_col_sums(sb200_matrix* m, double* out) {
+  ENTER(m);
+  return run_to_host(m, SWEEP_COLSUM, nullptr, 0, 0.0, out, m->ncol);
+}
+int sb200_row_sums(sb200_matrix* m, double* out) {
+  ENTER(m);
+  return run_to_host(m, SWEEP_ROWSUM, nullptr, 0, 0.0, out, m->nrow);
+}
+int sb200_col_means(sb200_matrix* m, double* out) {
+  ENTER(m);
+  // RcppSparse.h:148: sums[i] / Dim[0]; Dim[0] == 0 gives 0/0 = NaN there and here
+  if (m->nrow == 0) {
+    for (int32_t c = 0; c < m->ncol; ++c) out[c] = 0.0 / static_cast<double>(m->nrow);
+    return SB200_OK;
+  }
+  return run_to_host(m, SWEEP_COLSUM, nullptr, 0, static_cast<double>(m->nrow), out, m->ncol);
+}
+int sb200_row_means(sb200_matrix* m, double* out) {
+  ENTER(m);
+  if (m->ncol == 0) {
+    for (int32_t r = 0; r < m->nrow; ++r) out[r] = 0.0 / static_cast<double>(m->ncol);
+    return SB200_OK;
+  }
+  return run_to_host(m, SWEEP_ROWSUM, nullptr, 0, static_cast<double>(m->ncol), out, m->nrow);
+}
+int sb200_spmv(sb200_matrix* m, const double* v, double* y) {
+  ENTER(m);
+  return run_to_host(m, SWEEP_SPMV, v, m->ncol, 0.0, y, m->nrow);
+}
+int sb200_spmv_t(sb200_matrix* m, const double* v, double* y) {
+  ENTER(m);
+  return run_to_host(m, SWEEP_SPMV_T, v, m->nrow, 0.0, y, m->ncol);
+}
+
+int sb200_transpose(sb200_matrix* m, int32_t* p_out, int32_t* i_out, double* x_out) {
+  ENTER(m);
+  if (!p_out || (m->nnz > 0 && (!i_out || !x_out))) return fail(SB200_E_INVALID, "NULL output array");
+  sb200_matrix* t = nullptr;
+  SB_TRY(alloc_matrix(m->device, m->ncol, m->nrow, m->nnz, &t));
+  int rc = transpose_device(m, t->d_p, t->d_i, t->d_x);
+  cudaError_t e = cudaSuccess;
+  if (rc == SB200_OK) {
+    e = cudaMemcpyAsync(p_out, t->d_p, sizeof(int32_t) * (static_cast<size_t>(m->nrow) + 1), cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess && m->nnz > 0)
+      e = cudaMemcpyAsync(i_out, t->d_i, sizeof(int32_t) * static_cast<size_t>(m->nnz), cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess && m->nnz > 0)
+      e = cudaMemcpyAsync(x_out, t->d_x, sizeof(double) * static_cast<size_t>(m->nnz), cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+  }
+  free_matrix(t);
+  if (rc != SB200_OK) return rc;
+  if (e != cudaSuccess) return cuda_fail(e, "download of the transposed matrix", __FILE__, __LINE__);
+  return SB200_OK;
+}
+
+int sb200_algorithmic_bytes(const sb200_matrix* m, const char* op, int64_t* bytes) {
+  SB_TRY(check_handle(m));
+  if (!op || !bytes) return fail(SB200_E_INVALID, "NULL argument");
+  const int64_t N = m->nnz, n = m->ncol, r = m->nrow;
+  const std::string s(op);
+  // compulsory traffic only — every array once, the output once
+  if (s == "col_sums" || s == "col_means")
+    *bytes = 8 * N + 4 * (n + 1) + 8 * n;
+  else if (s == "row_sums" || s == "row_means")
+    *bytes = 12 * N + 8 * r;
+  else if (s == "spmv" || s == "spmv_t")
+    *bytes = 12 * N + 4 * (n + 1) + 8 * n + 8 * r;
+  else if (s == "transpose")
+    *bytes = 24 * N + 4 * (n + 1) + 4 * (r + 1);
+  else
+    return fail(SB200_E_INVALID, "unknown op '" + s + "'");
+  return SB200_OK;
+}
+
+int sb200_matrix_download_columns(sb200_matrix* m, int64_t c0, int64_t c1, int32_t* i_out, int32_t* p_out, double* x_out,
+                                  int64_t* nnz_out) {
+  ENTER(m);
+  if (c0 < 0 || c1 < c0 || c1 > m->ncol) return fail(SB200_E_INVALID, "column range outside the matrix");
+  int32_t ends[2] = {0, 0};
+  SB_CUDA(cudaMemcpyAsync(&ends[0], m->d_p + c0, sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+  SB_CUDA(cudaMemcpyAsync(&ends[1], m->d_p + c1, sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+  SB_CUDA(cudaStreamSynchronize(m->stream));
+  const int64_t k0 = ends[0], k1 = ends[1];
+  if (nnz_out) *nnz_out = k1 - k0;
+  if (!i_out) return SB200_OK;  // size query
+  if (!p_out || !x_out) return fail(SB200_E_INVALID, "NULL output array");
+  SB_CUDA(cudaMemcpyAsync(p_out, m->d_p + c0, sizeof(int32_t) * static_cast<size_t>(c1 - c0 + 1), cudaMemcpyDeviceToHost, m->stream));
+  if (k1 > k0) {
+    SB_CUDA(cudaMemcpyAsync(i_out, m->d_i + k0, sizeof(int32_t) * static_cast<size_t>(k1 - k0), cudaMemcpyDeviceToHost, m->stream));
+    SB_CUDA(cudaMemcpyAsync(x_out, m->d_x + k0, sizeof(double) * static_cast<size_t>(k1 - k0), cudaMemcpyDeviceToHost, m->stream));
+  }
+  SB_CUDA(cudaStreamSynchronize(m->stream));
+  for (int64_t c = 0; c <= c1 - c0; ++c) p_out[c] -= static_cast<int32_t>(k0);
+  return SB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+// Shared declarations of libsparse_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/sparse_b200.h"
+
+namespace sb200 {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: the C ABI never throws; every internal step returns a status.
+// ---------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define SB_CUDA(expr)                                                        \
+  do {                                                                       \
+    cudaError_t sb_e_ = (expr);                                              \
+    if (sb_e_ != cudaSuccess) return ::sb200::cuda_fail(sb_e_, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define SB_TRY(expr)              \
+  do {                            \
+    int sb_rc_ = (expr);          \
+    if (sb_rc_ != SB200_OK) return sb_rc_; \
+  } while (0)
+
+extern std::atomic<int64_t> g_launches;  // kernels launched by this library (sb200_launch_count)
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------------------------
+// geometry of the merge-path sweep (sweep.cu) — one "item" is either one stored entry or one
+// column end; a tile is SWEEP_TILE consecutive items on the merge path of (p[1..ncol], 0..nnz).
+// ---------------------------------------------------------------------------------------------
+constexpr int SWEEP_THREADS = 512;
+constexpr int SWEEP_IPT = 7;  // odd => conflict-free 8-byte shared-memory reads at stride IPT
+constexpr int SWEEP_TILE = SWEEP_THREADS * SWEEP_IPT;  // 3584 items
+
+constexpr int NUM_SMS_B200 = 148;
+
+// ---------------------------------------------------------------------------------------------
+// the device-resident mirror
+// ---------------------------------------------------------------------------------------------
+struct BandPlan;  // transpose.cu
+
+}  // namespace sb200
+
+struct sb200_matrix {
+  uint32_t magic;
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  bool owns_stream;
+  bool owns_arrays;
+  int32_t nrow, ncol;
+  int64_t nnz;
+  // mirror of the dgCMatrix slots (RcppSparse.h:29-30); allocations are padded so that 16-byte
+  // bulk copies starting at any 16-byte-aligned element may run to the next 16-byte boundary.
+  int32_t* d_i;
+  int32_t* d_p;
+  double* d_x;
+  // merge-path plan: plan[t] = number of column ends before diagonal t*SWEEP_TILE (t = 0..n_tiles)
+  int32_t* d_plan;
+  int64_t n_tiles;
+  // per-launch workspace (carries, tickets), zeroed where the kernels expect zero
+  void* d_ws;
+  size_t ws_bytes;
+  // device staging for the host-buffer entry points
+  double* d_stage_in;
+  double* d_stage_out;
+  int64_t stage_len;
+};
+
+namespace sb200 {
+
+constexpr uint32_t MATRIX_MAGIC = 0x5B200C5Cu;
+
+inline int check_handle(const sb200_matrix* m) {
+  if (m == nullptr || m->magic != MATRIX_MAGIC) return fail(SB200_E_INVALID, "not a live sb200_matrix handle");
+  return SB200_OK;
+}
+
+// RAII device switch for entry points
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// sweep.cu
+enum SweepMode { SWEEP_COLSUM = 0, SWEEP_SPMV_T = 1, SWEEP_ROWSUM = 2, SWEEP_SPMV = 3 };
+int build_sweep_plan(sb200_matrix* m);
+int launch_sweep(sb200_matrix* m, SweepMode mode, const double* d_v, double divisor, double* d_out);
+int launch_vec_div(cudaStream_t s, double* d, int64_t n, double divisor);
+
+// validate.cu
+int validate_structure(sb200_matrix* m);
+
+// scan.cu — exclusive prefix sum of u32 counts into int32 offsets (out has n+1 entries);
+// d_total (optional) receives the 64-bit grand total.  ws must hold scan_workspace_bytes(n).
+size_t scan_workspace_bytes(int64_t n);
+int exclusive_scan_u32(cudaStream_t s, const uint32_t* d_in, int32_t* d_out, int64_t n, unsigned long long* d_total,
+                       void* d_ws, size_t ws_bytes);
+
+// transpose.cu
+int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double* d_x_out);
+
+// mirror.cu
+int alloc_matrix(int device, int32_t nrow, int32_t ncol, int64_t nnz, sb200_matrix** out);  // owns arrays, uninitialised
+int finish_matrix(sb200_matrix* m, unsigned flags);  // validate + plan + workspace
+size_t padded_bytes(size_t bytes);
+
+}  // namespace sb200

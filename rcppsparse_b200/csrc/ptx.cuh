@@ -1,0 +1,96 @@
+// Thin inline-PTX wrappers used by the sm_100a kernels: mbarrier, 1-D bulk async copy
+// (cp.async.bulk, the TMA engine's non-tensor form; SASS: UBLKCP), cache-hinted loads/stores,
+// warp primitives.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb200 {
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
+}
+// make mbarrier.init visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ---- 1-D bulk copy global -> shared, completion counted on an mbarrier ---------------------------
+// dst and src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+// order prior generic-proxy accesses to shared memory before later async-proxy ones
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// ---- streaming loads / stores ---------------------------------------------------------------------
+__device__ __forceinline__ int ld_stream_s32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int4 ld_stream_v4s32(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ld_stream_v2f64(const double2* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+// fire-and-forget FP64 add at L2 (SASS: REDG.E.ADD.F64)
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- warp helpers -----------------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ double shfl_up_f64(double v, int delta) { return __shfl_up_sync(0xffffffffu, v, delta); }
+
+}  // namespace ptx
+}  // namespace sb200

@@ -1,0 +1,151 @@
+"""Column sharding of one dgCMatrix across the ranks of a torch.distributed group.
+
+The reference is single-process (no parallelism on the hot path); the
+sweeps shard naturally because columns are independent units:
+
+  * each rank holds a contiguous, nnz-balanced COLUMN BLOCK — itself a valid dgCMatrix with
+    the full row count and p rebased to 0 — as one device-resident mirror (DeviceMatrix);
+  * column-indexed results (colSums, colMeans, A^T v) are disjoint slices: no arithmetic across
+    ranks, one all-gather to assemble the vector on every rank;
+  * row-indexed results (rowSums, rowMeans, A v) are full-length partials: one all-reduce (sum)
+    of 8*nrow bytes; mean scaling by the GLOBAL ncol happens after the reduce.
+
+One process per GPU (torchrun); NCCL over NVLink on GPUs, gloo in the CPU tests.  The local
+compute is behind a tiny protocol (``LocalSweeps``) so the host-side logic — the split, the
+slice bookkeeping, the collectives — is testable at world_size 2 without a GPU.
+"""
+from __future__ import annotations
+
+from typing import Protocol, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def split_columns_by_nnz(p: np.ndarray, world: int) -> list[int]:
+    """Column boundaries b[0..world] with p[b[k]] ~= k*nnz/world (binary search in p).
+    A column is never split; boundaries are non-decreasing; b[0]=0, b[world]=ncol."""
+    ncol = int(p.shape[0]) - 1
+    nnz = int(p[ncol])
+    bounds = [0]
+    for k in range(1, world):
+        target = (nnz * k) // world
+        c = int(np.searchsorted(p, target, side="left"))
+        c = min(max(c, bounds[-1]), ncol)
+        bounds.append(c)
+    bounds.append(ncol)
+    return bounds
+
+
+def split_columns_evenly(ncol: int, world: int) -> list[int]:
+    return [(ncol * k) // world for k in range(world + 1)]
+
+
+class LocalSweeps(Protocol):
+    """What a rank's column block must offer; tensors live on the rank's device."""
+
+    nrow: int
+    ncol: int
+
+    def col_sums(self, out: torch.Tensor, divisor: float) -> None: ...
+    def row_sums(self, out: torch.Tensor) -> None: ...
+    def spmv(self, v_local: torch.Tensor, out: torch.Tensor) -> None: ...
+    def spmv_t(self, v: torch.Tensor, out: torch.Tensor) -> None: ...
+    def div(self, t: torch.Tensor, divisor: float) -> None: ...
+
+
+class GpuLocal:
+    """LocalSweeps over a DeviceMatrix: every method is a kernel launch on torch's current stream."""
+
+    def __init__(self, dm):
+        self.dm = dm
+        self.nrow, self.ncol = dm.nrow, dm.ncol
+        dm.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def col_sums(self, out, divisor):
+        self.dm.col_sums_dev(out, divisor)
+
+    def row_sums(self, out):
+        self.dm.row_sums_dev(out, 0.0)
+
+    def spmv(self, v_local, out):
+        self.dm.spmv_dev(v_local, out)
+
+    def spmv_t(self, v, out):
+        self.dm.spmv_t_dev(v, out)
+
+    def div(self, t, divisor):
+        self.dm.vec_div_dev(t, t.numel(), divisor)
+
+
+class ShardedMatrix:
+    """The reference's Matrix methods (RcppSparse.h:131-156 + the SpMV idiom) over a column-sharded matrix.
+    Every method returns the FULL result vector on every rank."""
+
+    def __init__(self, local: LocalSweeps, bounds: Sequence[int], rank: int, group=None, device=None):
+        self.local = local
+        self.bounds = list(bounds)
+        self.world = len(self.bounds) - 1
+        self.rank = rank
+        self.group = group
+        self.nrow = local.nrow
+        self.ncol = self.bounds[-1]
+        self.c0, self.c1 = self.bounds[rank], self.bounds[rank + 1]
+        if local.ncol != self.c1 - self.c0:
+            raise ValueError("local block does not match its column range")
+        self.device = device if device is not None else torch.device("cpu")
+        self._counts = [self.bounds[k + 1] - self.bounds[k] for k in range(self.world)]
+        self._even = len(set(self._counts)) == 1
+        self._col_full = torch.empty(self.ncol, dtype=torch.float64, device=self.device)
+        self._row_full = torch.empty(self.nrow, dtype=torch.float64, device=self.device)
+
+    # ---- column-indexed: disjoint slices + all-gather --------------------------------------------------
+    def _gather_columns(self) -> torch.Tensor:
+        mine = self._col_full[self.c0:self.c1]
+        if self.world == 1:
+            return self._col_full
+        if self._even:
+            dist.all_gather_into_tensor(self._col_full, mine.clone(), group=self.group)
+        else:
+            parts = [self._col_full[self.bounds[k]:self.bounds[k + 1]] for k in range(self.world)]
+            # uneven counts: one broadcast per owner (grouped by the backend)
+            for k in range(self.world):
+                if parts[k].numel():
+                    dist.broadcast(parts[k], src=dist.get_global_rank(self.group, k) if self.group else k,
+                                   group=self.group)
+        return self._col_full
+
+    def colSums(self) -> torch.Tensor:
+        self.local.col_sums(self._col_full[self.c0:self.c1], 0.0)
+        return self._gather_columns()
+
+    def colMeans(self) -> torch.Tensor:
+        self.local.col_sums(self._col_full[self.c0:self.c1], float(self.nrow))  # nrow is global already
+        return self._gather_columns()
+
+    def spmv_t(self, v: torch.Tensor) -> torch.Tensor:
+        """A^T v: v[nrow] replicated on every rank."""
+        self.local.spmv_t(v, self._col_full[self.c0:self.c1])
+        return self._gather_columns()
+
+    # ---- row-indexed: full-length partials + all-reduce ----------------------------------------------------
+    def _reduce_rows(self) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(self._row_full, op=dist.ReduceOp.SUM, group=self.group)
+        return self._row_full
+
+    def rowSums(self) -> torch.Tensor:
+        self.local.row_sums(self._row_full)
+        return self._reduce_rows()
+
+    def rowMeans(self) -> torch.Tensor:
+        self.local.row_sums(self._row_full)
+        out = self._reduce_rows()
+        self.local.div(out, float(self.ncol))  # GLOBAL ncol (RcppSparse.h:154 divides by Dim[1])
+        return out
+
+    def spmv(self, v: torch.Tensor) -> torch.Tensor:
+        """A v: v[ncol] replicated; each rank uses only its own slice."""
+        self.local.spmv(v[self.c0:self.c1], self._row_full)
+        return self._reduce_rows()

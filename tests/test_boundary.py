@@ -1,0 +1,93 @@
+"""CPU-side checks of the drop-in boundary (no GPU, no compute calls):
+the shared library loads, exports exactly what include/sparse_b200.h declares, fails loudly
+without a device, and the product never touches oracle/."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sparse_b200.h")
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from rcppsparse_b200 import build
+
+    return build.build_library()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_what_the_binding_binds():
+    from rcppsparse_b200 import _lib
+
+    assert declared_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", built_lib], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (sb200_[a-z0-9_]+)", out))
+    missing = [s for s in declared_symbols() if s not in exported]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    lib = ctypes.CDLL(built_lib)
+    for s in declared_symbols():
+        getattr(lib, s)
+
+
+def test_library_loads_and_reports_abi(built_lib):
+    from rcppsparse_b200 import _lib
+
+    L = _lib.lib()
+    assert L.sb200_abi_version() == 1
+    assert isinstance(L.sb200_last_error(), bytes)
+    assert L.sb200_launch_count() >= 0
+
+
+def test_no_device_is_an_error_not_a_fallback(built_lib):
+    """On a box without a GPU every entry that would compute must fail with SB200_E_NODEVICE."""
+    import numpy as np
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from rcppsparse_b200 import Matrix, SparseB200Error, _lib
+
+    assert _lib.device_count() == 0
+    m = Matrix(np.array([1.0]), np.array([0], np.int32), np.array([0, 1], np.int32), np.array([1, 1], np.int32))
+    with pytest.raises(SparseB200Error) as ei:
+        m.colSums()
+    assert ei.value.code == _lib.E_NODEVICE
+    assert "no CPU fallback" in ei.value.message or "no CUDA device" in ei.value.message
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing in the package, the header or the C sources may name it."""
+    pat = re.compile(r"\boracle\b|liboracle|oport_|oref_")
+    offenders = []
+    for base in (os.path.join(ROOT, "rcppsparse_b200"), os.path.join(ROOT, "include")):
+        for dp, _, files in os.walk(base):
+            if os.path.basename(dp) in ("build", "__pycache__"):
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".c")):
+                    text = open(os.path.join(dp, f), errors="replace").read()
+                    for ln, line in enumerate(text.splitlines(), 1):
+                        if pat.search(line) and "the CPU oracle can be fed" not in line:
+                            offenders.append(f"{os.path.relpath(os.path.join(dp, f), ROOT)}:{ln}: {line.strip()}")
+    assert not offenders, "\n".join(offenders)
+
+
+def test_missing_library_raises(monkeypatch, tmp_path):
+    from rcppsparse_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError):
+        _lib.lib()

@@ -1,0 +1,251 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (host-buffer entry points, the same
+ones include/RcppSparse.h calls), against the oracle on identical inputs.
+
+Bar (BASELINE.json north_star): transpose structure p/i and the permuted values bit-exact;
+FP64 reductions within |delta| <= 1e-12 * sum|a_ij| (|a_ij * v_j| for SpMV) per output entry.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from rcppsparse_b200 import DeviceMatrix, Matrix, SparseB200Error, _lib, columnSums, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12  # north_star tolerance
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+@pytest.fixture(scope="module")
+def checker():
+    return oracle.best()  # the compiled reference when it travelled to this box, else the C port
+
+
+def as_matrix(g):
+    return Matrix(g["x"], g["i"], g["p"], g["dim"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# committed golden vectors (produced by the reference's own compiled code, tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------------
+def test_golden_reductions(golden):
+    g = golden
+    A = as_matrix(g)
+    args = (g["i"], g["p"], g["x"], g["nrow"], g["ncol"])
+    for op, got in (("colSums", A.colSums()), ("rowSums", A.rowSums()), ("colMeans", A.colMeans()),
+                    ("rowMeans", A.rowMeans()), ("columnSums", columnSums(A))):
+        oracle.assert_within(op, got, g[op], *args, tol=TOL)
+    A.release()
+
+
+def test_golden_spmv(golden):
+    g = golden
+    A = as_matrix(g)
+    args = (g["i"], g["p"], g["x"], g["nrow"], g["ncol"])
+    oracle.assert_within("spmv", A.spmv(g["v_col"]), g["spmv"], *args, v=g["v_col"], tol=TOL)
+    oracle.assert_within("spmv_t", A.spmv_t(g["v_row"]), g["spmv_t"], *args, v=g["v_row"], tol=TOL)
+    A.release()
+
+
+def test_golden_transpose_bit_exact(golden):
+    g = golden
+    A = as_matrix(g)
+    T = A.transpose()
+    assert T.Dim.tolist() == [g["ncol"], g["nrow"]]
+    assert np.array_equal(T.p, g["t_p"]), "p' differs"
+    assert np.array_equal(T.i, g["t_i"]), "i' differs (order inside a column must be ascending)"
+    assert np.array_equal(bits(T.x), bits(g["t_x"])), "x' must be a bit-exact permutation"
+    assert A.t().p.tolist() == g["t_p"].tolist()  # the vignette's .t() alias
+    A.release()
+
+
+def test_vignette_known_answers_on_gpu():
+    """The only literal matrix in the reference tree (vignettes/Documentation.Rmd:213-216)."""
+    A = Matrix(np.array([0.41, 0.35, 0.84, 0.37, 0.26]), np.array([0, 2, 0, 1, 1], np.int32),
+               np.array([0, 0, 1, 2, 4, 5], np.int32), np.array([5, 5], np.int32))
+    assert A.colSums().tolist() == [0.0, 0.41, 0.35, 1.21, 0.26]
+    assert A.rowSums().tolist() == [1.25, 0.63, 0.35, 0.0, 0.0]
+    assert A.colMeans().tolist() == [0.0, 0.08199999999999999, 0.069999999999999993, 0.24199999999999999,
+                                     0.052000000000000005]
+    T = A.transpose()
+    assert T.p.tolist() == [0, 2, 4, 5, 5, 5] and T.i.tolist() == [1, 3, 3, 4, 2]
+    assert T.x.tolist() == [0.41, 0.84, 0.37, 0.26, 0.35]
+
+
+# ---------------------------------------------------------------------------------------------------
+# seeded synthetic matrices at sizes the oracle finishes in seconds
+# ---------------------------------------------------------------------------------------------------
+SYNTH_CASES = {
+    "C1_full": lambda: synth.config("C1"),                      # 10k x 10k, 1e6 nnz — BASELINE configs[0]
+    "C2_scaled": lambda: synth.config("C2", 0.05),              # 1M x 5k, 5e6 nnz
+    "C3_scaled": lambda: synth.config("C3", 0.004),             # 30k x 4k, ~6e6 nnz, banded row popularity
+    "C4_scaled": lambda: synth.config("C4", 0.003),             # 2^20 x 6k power-law columns
+    "many_tiny_columns": lambda: synth.powerlaw_spec(5000, 300_000, 2.0, 77, empty_permille=400),
+    "few_huge_columns": lambda: synth.uniform_spec(400_000, 7, 0.9, 78),
+    "tall_sparse": lambda: synth.uniform_spec(3_000_000, 64, 0.01, 79),
+}
+
+
+@pytest.fixture(scope="module", params=sorted(SYNTH_CASES))
+def synth_case(request):
+    spec = SYNTH_CASES[request.param]()
+    i, p, x = synth.generate_host(spec)
+    return request.param, spec, i, p, x
+
+
+def test_synth_device_generator_matches_host_bitwise(synth_case):
+    name, spec, i, p, x = synth_case
+    with DeviceMatrix.synth(spec) as D:
+        di, dp, dx = D.download_columns()
+    assert np.array_equal(dp, p) and np.array_equal(di, i) and np.array_equal(bits(dx), bits(x)), name
+
+
+def test_synth_reductions_and_spmv(synth_case, checker):
+    name, spec, i, p, x = synth_case
+    nrow, ncol = spec.nrow, spec.ncol
+    A = Matrix(x, i, p, np.array([nrow, ncol], np.int32))
+    args = (i, p, x, nrow, ncol)
+    worst = {}
+    for op in ("colSums", "rowSums", "colMeans", "rowMeans"):
+        worst[op] = oracle.assert_within(op, getattr(A, op)(), getattr(checker, op)(*args), *args, tol=TOL)
+    v_col, v_row = synth.dense_vector(spec.seed, ncol), synth.dense_vector(spec.seed + 7, nrow)
+    worst["spmv"] = oracle.assert_within("spmv", A.spmv(v_col), checker.spmv(*args, v_col), *args, v=v_col, tol=TOL)
+    worst["spmv_t"] = oracle.assert_within("spmv_t", A.spmv_t(v_row), checker.spmv_t(*args, v_row), *args, v=v_row,
+                                           tol=TOL)
+    print(name, {k: f"{v:.2e}" for k, v in worst.items()})
+    A.release()
+
+
+def test_synth_transpose_bit_exact(synth_case, checker):
+    name, spec, i, p, x = synth_case
+    nrow, ncol = spec.nrow, spec.ncol
+    A = Matrix(x, i, p, np.array([nrow, ncol], np.int32))
+    T = A.transpose()
+    ti, tp, tx = checker.transpose(i, p, x, nrow, ncol)
+    assert np.array_equal(T.p, tp), name
+    assert np.array_equal(T.i, ti), name
+    assert np.array_equal(bits(T.x), bits(tx)), name
+    A.release()
+
+
+@pytest.mark.parametrize("bands", [1, 2, 7, 64, 300])
+def test_transpose_is_independent_of_band_count(bands, monkeypatch, checker):
+    """The band decomposition is an implementation detail: any band count gives the same bits."""
+    spec = synth.powerlaw_spec(6000, 3000, 300.0, 91, row_levels=8)
+    i, p, x = synth.generate_host(spec)
+    monkeypatch.setenv("SB200_TRANSPOSE_BANDS", str(bands))
+    T = Matrix(x, i, p, np.array([spec.nrow, spec.ncol], np.int32)).transpose()
+    ti, tp, tx = checker.transpose(i, p, x, spec.nrow, spec.ncol)
+    assert np.array_equal(T.p, tp) and np.array_equal(T.i, ti) and np.array_equal(bits(T.x), bits(tx))
+
+
+# ---------------------------------------------------------------------------------------------------
+# properties that hold at any size (used again at BASELINE sizes in test_fullsize_gpu.py)
+# ---------------------------------------------------------------------------------------------------
+def test_transpose_round_trip_and_cross_identities():
+    spec = synth.config("C3", 0.01)
+    with DeviceMatrix.synth(spec) as D:
+        i, p, x = D.download_columns()
+        with D.transpose_dev() as T, T.transpose_dev() as TT:
+            i2, p2, x2 = TT.download_columns()
+            assert np.array_equal(p2, p) and np.array_equal(i2, i) and np.array_equal(bits(x2), bits(x))
+            # rowSums(A) == colSums(A^T) and A v == (A^T)^T v, within tolerance
+            feed_r = np.bincount(i, weights=np.abs(x), minlength=spec.nrow)
+            assert np.all(np.abs(D.row_sums() - T.col_sums()) <= 2 * TOL * feed_r)
+            v = synth.dense_vector(5, spec.ncol)
+            col_of = np.repeat(np.arange(spec.ncol), np.diff(p))
+            feed_v = np.bincount(i, weights=np.abs(x * v[col_of]), minlength=spec.nrow)
+            assert np.all(np.abs(D.spmv(v) - T.spmv_t(v)) <= 2 * TOL * feed_v)
+
+
+def test_colsums_bit_stable_run_to_run():
+    """The column sweep uses no atomics: identical bits on every run (also a cheap race detector)."""
+    spec = synth.config("C4", 0.002)
+    with DeviceMatrix.synth(spec) as D:
+        first = D.col_sums()
+        v = synth.dense_vector(3, spec.nrow)
+        first_t = D.spmv_t(v)
+        for _ in range(5):
+            assert np.array_equal(bits(D.col_sums()), bits(first))
+            assert np.array_equal(bits(D.spmv_t(v)), bits(first_t))
+
+
+def test_spmv_linearity():
+    spec = synth.config("C2", 0.02)
+    with DeviceMatrix.synth(spec) as D:
+        i, p, x = D.download_columns()
+        a, b = synth.dense_vector(11, spec.ncol), synth.dense_vector(12, spec.ncol)
+        col_of = np.repeat(np.arange(spec.ncol), np.diff(p))
+        feed = np.bincount(i, weights=np.abs(x) * (np.abs(2 * a[col_of]) + np.abs(3 * b[col_of])), minlength=spec.nrow)
+        lhs = D.spmv(2 * a - 3 * b)
+        rhs = 2 * D.spmv(a) - 3 * D.spmv(b)
+        assert np.all(np.abs(lhs - rhs) <= 4 * TOL * feed + 1e-300)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference semantics around the sweeps
+# ---------------------------------------------------------------------------------------------------
+def test_view_aliases_host_memory_and_refresh():
+    """Reference vignettes/Documentation.Rmd:325-347: the Matrix is a view; in-place edits are seen."""
+    x = np.array([1.0, 2.0, 3.0])
+    A = Matrix(x, np.array([0, 1, 0], np.int32), np.array([0, 2, 3], np.int32), np.array([2, 2], np.int32))
+    assert A.x is x
+    assert A.colSums().tolist() == [3.0, 3.0]
+    x[0] = 999.0
+    A.refresh()
+    assert A.colSums().tolist() == [1001.0, 3.0]
+    B = A.clone()
+    B.x[0] = -1.0
+    assert A.x[0] == 999.0  # clone() is a deep copy (RcppSparse.h:54-60)
+
+
+def test_from_s4_and_exported_function_accept_scipy_csc():
+    import scipy.sparse as sp
+
+    a = sp.random(300, 200, density=0.05, format="csc", random_state=3, dtype=np.float64)
+    a.sort_indices()
+    got = columnSums(a)
+    want = np.asarray(a.sum(axis=0)).ravel()
+    assert np.allclose(got, want, rtol=0, atol=1e-12 * np.abs(a).sum(axis=0).max())
+
+    class NotS4:
+        x = 1
+
+    with pytest.raises(ValueError, match="Cannot construct RcppSparse::Matrix"):
+        Matrix.from_S4(NotS4())
+
+
+@pytest.mark.parametrize("what", ["row_out_of_range", "negative_row", "p0", "p_last", "p_decreasing", "unsorted_rows",
+                                  "duplicate_rows"])
+def test_corrupt_structure_is_an_error_not_ub(what):
+    """Reference: Rcpp::index_out_of_bounds from the checked sums(i[j]) (RcppSparse.h:142).  Here: SB200_E_STRUCTURE."""
+    i = np.array([0, 2, 1, 3], np.int32)
+    p = np.array([0, 2, 4], np.int32)
+    x = np.ones(4)
+    if what == "row_out_of_range":
+        i[1] = 4
+    elif what == "negative_row":
+        i[0] = -1
+    elif what == "p0":
+        p[0] = 1
+    elif what == "p_last":
+        p[2] = 3
+    elif what == "p_decreasing":
+        p[1] = 5
+    elif what == "unsorted_rows":
+        i[:2] = [2, 0]
+    elif what == "duplicate_rows":
+        i[:2] = [2, 2]
+    with pytest.raises(SparseB200Error) as ei:
+        Matrix(x, i, p, np.array([4, 2], np.int32)).rowSums()
+    assert ei.value.code == _lib.E_STRUCTURE
+
+
+def test_launch_counter_counts_kernels():
+    before = _lib.lib().sb200_launch_count()
+    A = Matrix(np.array([1.0]), np.array([0], np.int32), np.array([0, 1], np.int32), np.array([1, 1], np.int32))
+    A.colSums()
+    assert _lib.lib().sb200_launch_count() > before

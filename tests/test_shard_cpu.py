@@ -1,0 +1,111 @@
+"""Host-side logic of the column-sharding layer at world_size 2 over gloo (no GPU):
+the split, the slice bookkeeping and the collectives.  The rank-local compute is an
+oracle-backed stand-in for the CUDA kernels, injected through the LocalSweeps protocol."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle
+from rcppsparse_b200 import shard, synth
+
+
+class OracleLocal:
+    """LocalSweeps on CPU tensors, computed by the C port (test stand-in for GpuLocal)."""
+
+    def __init__(self, i, p, x, nrow, ncol):
+        self.i, self.p, self.x, self.nrow, self.ncol = i, p, x, nrow, ncol
+        self.o = oracle.Port()
+
+    def col_sums(self, out, divisor):
+        r = self.o.colSums(self.i, self.p, self.x, self.nrow, self.ncol)
+        out.copy_(torch.from_numpy(r / divisor if divisor else r))
+
+    def row_sums(self, out):
+        out.copy_(torch.from_numpy(self.o.rowSums(self.i, self.p, self.x, self.nrow, self.ncol)))
+
+    def spmv(self, v_local, out):
+        out.copy_(torch.from_numpy(self.o.spmv(self.i, self.p, self.x, self.nrow, self.ncol, v_local.numpy())))
+
+    def spmv_t(self, v, out):
+        out.copy_(torch.from_numpy(self.o.spmv_t(self.i, self.p, self.x, self.nrow, self.ncol, v.numpy())))
+
+    def div(self, t, divisor):
+        t.div_(divisor)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, balanced, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        spec = synth.powerlaw_spec(700, 240, 30.0, 99, row_levels=4)
+        i, p, x = synth.generate_host(spec)
+        bounds = shard.split_columns_by_nnz(p, world) if balanced else shard.split_columns_evenly(spec.ncol, world)
+        c0, c1 = bounds[rank], bounds[rank + 1]
+        # a rank's block can be generated independently of the others (weak-scaling benches do this)
+        bi, bp, bx = synth.generate_host(spec, c0, c1)
+        assert np.array_equal(bp, p[c0:c1 + 1] - p[c0]) and np.array_equal(bi, i[p[c0]:p[c1]])
+        S = shard.ShardedMatrix(OracleLocal(bi, bp, bx, spec.nrow, c1 - c0), bounds, rank)
+        full = oracle.Port()
+        args = (i, p, x, spec.nrow, spec.ncol)
+        v_c = torch.from_numpy(synth.dense_vector(1, spec.ncol))
+        v_r = torch.from_numpy(synth.dense_vector(2, spec.nrow))
+        checks = {
+            "colSums": (S.colSums().numpy().copy(), full.colSums(*args), None),
+            "colMeans": (S.colMeans().numpy().copy(), full.colMeans(*args), None),
+            "rowSums": (S.rowSums().numpy().copy(), full.rowSums(*args), None),
+            "rowMeans": (S.rowMeans().numpy().copy(), full.rowMeans(*args), None),
+            "spmv": (S.spmv(v_c).numpy().copy(), full.spmv(*args, v_c.numpy()), v_c.numpy()),
+            "spmv_t": (S.spmv_t(v_r).numpy().copy(), full.spmv_t(*args, v_r.numpy()), v_r.numpy()),
+        }
+        for op, (got, want, v) in checks.items():
+            oracle.assert_within(op, got, want, *args, v=v)
+        q.put((rank, "ok", bounds))
+    except Exception as e:  # surface the failure in the parent
+        q.put((rank, f"FAIL {type(e).__name__}: {e}", None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("balanced", [True, False])
+def test_sharded_sweeps_world2_gloo(balanced):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, balanced, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert all(r[1] == "ok" for r in results), results
+
+
+def test_split_by_nnz_balances_and_covers():
+    spec = synth.powerlaw_spec(5000, 2000, 80.0, 5)
+    _, p, _ = synth.generate_host(spec)
+    for world in (1, 2, 3, 8):
+        b = shard.split_columns_by_nnz(p, world)
+        assert b[0] == 0 and b[-1] == spec.ncol and all(b[k] <= b[k + 1] for k in range(world))
+        per = [int(p[b[k + 1]] - p[b[k]]) for k in range(world)]
+        assert sum(per) == int(p[-1])
+        longest = int(np.diff(p).max())
+        assert max(per) - min(per) <= 2 * longest + 1  # never splits a column, so off by at most one column each side
+
+
+def test_split_handles_degenerate_matrices():
+    assert shard.split_columns_by_nnz(np.zeros(1, np.int32), 4) == [0, 0, 0, 0, 0]       # ncol = 0
+    assert shard.split_columns_by_nnz(np.zeros(6, np.int32), 2) == [0, 0, 5]             # all columns empty
+    assert shard.split_columns_evenly(10, 4) == [0, 2, 5, 7, 10]
