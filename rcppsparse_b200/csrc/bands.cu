@@ -1,0 +1,850 @@
+// Row-banded kernels: the CSC -> CSR transpose and the row-indexed sweeps (rowSums, rowMeans, A v).
+//
+// Replaces, from the reference (zdebruine/RcppSparse):
+//   Matrix::transpose()   RcppSparse.h:375-385 (arithmetic = R's Matrix::t, a serial counting sort)
+//   Matrix::rowSums()     RcppSparse.h:138-144   sums(i[j]) += x[j]
+//   Matrix::rowMeans()    RcppSparse.h:151-156
+//   A v (iterator idiom)  y[it.row()] += it.value() * v[col]   (shape of :140-142)
+//
+// Why bands.  A row-indexed result of 1e6 doubles does not fit shared memory, and one L2 atomic
+// per stored entry tops out at ~160 G RED.F64/s on B200 (profiles/r01/microbench: 31% of the
+// rowSums roofline).  But rows are SORTED inside every column, so the entries of a column that fall
+// in a row band [rb[b], rb[b+1]) are one contiguous run.  A band plan (built once per matrix
+// structure, cached in the handle) stores for each band b and column c where that run starts
+// ("band pointers").  CTA (b, h) then owns band b for column split h: it streams only its runs,
+// keeps the band's rows in shared memory — accumulators for the sums, append cursors for the
+// transpose — and nobody else ever touches those rows.  Neighbouring bands read neighbouring runs of
+// the same columns at about the same time, so partially used 32-byte sectors are served from L2.
+//
+// Plan (one pass each, HBM-bound):
+//   P1  histogram of row indices per column split (stream i, 4 B/nnz; counts privatised in shared
+//       memory when u32[nrow*S] fits) -> exclusive scan (scan.cu) -> p' and per-split offsets
+//   P2  band boundaries: nb bands of ~equal nnz, bounded in rows (binary searches in p')
+//   P3  band pointers over the merge-path tiles of the sweeps (stream i again, 4 B/nnz)
+//
+// Inner skeleton (both kernels): a warp takes 32 consecutive columns of a chunk, one run descriptor
+// per lane, flattens the runs with a shuffle scan, and walks the concatenated entries 32 at a time,
+// so consecutive lanes read consecutive entries of a run (coalesced).
+//   * sums:      acc[row - rb[b]] += x (* v[col])  shared-memory FP64 atomic; at the end the band's
+//                accumulators are added to the result with coalesced REDs (plain stores when S = 1)
+//   * transpose: pass 1 counts entries per (warp, row); a per-row scan over the 16 warps gives every
+//                warp its private, ordered slot range; pass 2 re-walks the entries, ranks equal rows
+//                inside a 32-entry step with match.any in lane order (= source column order) and
+//                stores column id and value.  Order inside an output row is source-column order by
+//                construction => bit-exact canonical CSC of A^T, no sort, no global atomics.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <new>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sb200 {
+
+namespace {
+
+// ================================================================================================
+// P1: per-split row histogram
+// ================================================================================================
+constexpr int HIST_THREADS = 512;
+constexpr int HIST_SMEM_MAX_WORDS = 48 * 1024;  // u32 counters, 192 KB
+
+// cnt[r * S + h] += number of entries with row r in column split h.  CTA (h, g): slice g of split h.
+template <bool PRIVATE>
+__global__ void __launch_bounds__(HIST_THREADS)
+    row_hist_kernel(const int32_t* __restrict__ gi, const int32_t* __restrict__ gp, const int32_t* __restrict__ cs,
+                    int S, int ctas_per_split, int32_t nrow, uint32_t* __restrict__ cnt) {
+  extern __shared__ uint32_t hsm[];
+  const int h = blockIdx.x / ctas_per_split, g = blockIdx.x % ctas_per_split;
+  if (PRIVATE) {
+    for (int r = threadIdx.x; r < nrow; r += HIST_THREADS) hsm[r] = 0u;
+    __syncthreads();
+  }
+  const int64_t k_lo = gp[cs[h]], k_hi = gp[cs[h + 1]];
+  // slice boundaries on multiples of 4 entries inside [k_lo, k_hi) so the body can use 128-bit loads
+  const int64_t a_lo = (k_lo + 3) & ~int64_t(3), a_hi = k_hi & ~int64_t(3);
+  auto bump = [&](int32_t r) {
+    if (PRIVATE)
+      atomicAdd(&hsm[r], 1u);
+    else
+      ptx::red_add_u32(cnt + static_cast<int64_t>(r) * S + h, 1u);
+  };
+  if (a_lo < a_hi) {
+    const int64_t n4 = (a_hi - a_lo) >> 2;
+    const int64_t g_begin = (n4 * g) / ctas_per_split, g_end = (n4 * (g + 1)) / ctas_per_split;
+    const int4* __restrict__ i4 = reinterpret_cast<const int4*>(gi + a_lo);
+    for (int64_t q = g_begin + threadIdx.x; q < g_end; q += HIST_THREADS) {
+      const int4 r = ptx::ld_stream_v4s32(i4 + q);
+      bump(r.x);
+      bump(r.y);
+      bump(r.z);
+      bump(r.w);
+    }
+    if (g == 0) {  // ragged head and tail of the split
+      for (int64_t k = k_lo + threadIdx.x; k < a_lo && k < k_hi; k += HIST_THREADS) bump(gi[k]);
+      for (int64_t k = a_hi + threadIdx.x; k < k_hi; k += HIST_THREADS) bump(gi[k]);
+    }
+  } else if (g == 0) {
+    for (int64_t k = k_lo + threadIdx.x; k < k_hi; k += HIST_THREADS) bump(gi[k]);
+  }
+  if (PRIVATE) {
+    __syncthreads();
+    for (int r = threadIdx.x; r < nrow; r += HIST_THREADS) {
+      const uint32_t c = hsm[r];
+      if (c) ptx::red_add_u32(cnt + static_cast<int64_t>(r) * S + h, c);
+    }
+  }
+}
+
+// column split boundaries: cs[h] = first column whose start offset reaches h * nnz / S
+__global__ void split_bounds_kernel(const int32_t* __restrict__ gp, int32_t ncol, int64_t nnz, int S,
+                                    int32_t* __restrict__ cs) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h > S) return;
+  if (h == 0) {
+    cs[0] = 0;
+    return;
+  }
+  if (h == S) {
+    cs[S] = ncol;
+    return;
+  }
+  const int64_t target = (nnz * h) / S;
+  int32_t lo = 0, hi = ncol;
+  while (lo < hi) {
+    const int32_t mid = lo + ((hi - lo) >> 1);
+    if (gp[mid] < target)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  cs[h] = lo;
+}
+
+// rowptr[r] = scan[r * S] (the scan runs over (row, split) pairs, row-major)
+__global__ void extract_rowptr_kernel(const int32_t* __restrict__ scan, int32_t nrow, int S, int32_t* __restrict__ rowptr) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r <= nrow; r += stride)
+    rowptr[r] = scan[r * S];
+}
+
+// ================================================================================================
+// P2: band boundaries.  key(r) = (1-eps) * p'[r]/nnz + eps * r/nrow is non-decreasing; band b starts
+// at the first row whose key reaches b/nb.  eps > 0 bounds the rows of a band (shared memory).
+// ================================================================================================
+__global__ void band_bounds_kernel(const int32_t* __restrict__ rowptr, int32_t nrow, int64_t nnz, int nb, double eps,
+                                   int32_t* __restrict__ rb) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nb) return;
+  int32_t r;
+  if (b == 0) {
+    r = 0;
+  } else if (b == nb) {
+    r = nrow;
+  } else {
+    const double wa = (1.0 - eps) / static_cast<double>(nnz);
+    const double wb = eps / static_cast<double>(nrow);
+    const double target = static_cast<double>(b) / static_cast<double>(nb);
+    int32_t lo = 0, hi = nrow;
+    while (lo < hi) {
+      const int32_t mid = lo + ((hi - lo) >> 1);
+      const double key = static_cast<double>(rowptr[mid]) * wa + static_cast<double>(mid) * wb;
+      if (key < target)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    r = lo;
+  }
+  rb[b] = r;
+}
+
+__global__ void band_max_rows_kernel(const int32_t* __restrict__ rb, int nb, int32_t* __restrict__ max_rows) {
+  int32_t mx = 0;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    const int32_t d = rb[b + 1] - rb[b];
+    mx = d > mx ? d : mx;
+  }
+  atomicMax(max_rows, mx);
+}
+
+// ================================================================================================
+// P3: band pointers over merge-path tiles (same plan as the sweeps: SWEEP_TILE items per tile)
+// bpt[(b-1)*ncol + c] = first k in column c with i[k] >= rb[b], for b = 1..nb-1
+// ================================================================================================
+constexpr int BP_THREADS = 256;
+constexpr int BP_IPT = SWEEP_TILE / BP_THREADS;
+static_assert(BP_THREADS * BP_IPT == SWEEP_TILE, "band-pointer tiling must match the sweep plan");
+
+__global__ void __launch_bounds__(BP_THREADS)
+    band_ptr_kernel(const int32_t* __restrict__ gi, const int32_t* __restrict__ gp, const int32_t* __restrict__ plan,
+                    int64_t n_tiles, int32_t ncol, int32_t nnz, const int32_t* __restrict__ rb, int nb,
+                    int32_t* __restrict__ bpt) {
+  extern __shared__ int32_t sm[];
+  int32_t* as = sm;                      // as[j] = p[c0 + j], j = 0..nc+1   (SWEEP_TILE + 2)
+  int32_t* is = sm + (SWEEP_TILE + 4);   // is[j] = i[k0 - 1 + j]            (SWEEP_TILE + 1)
+  int32_t* rbs = is + (SWEEP_TILE + 4);  // rbs[b] = rb[b], b = 0..nb
+  for (int b = threadIdx.x; b <= nb; b += BP_THREADS) rbs[b] = rb[b];
+  const int64_t total_items = static_cast<int64_t>(ncol) + nnz;
+
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    __syncthreads();  // previous tile fully consumed (also covers the rbs fill)
+    const int32_t c0 = plan[t], c1 = plan[t + 1];
+    const int64_t d0 = t * SWEEP_TILE;
+    int64_t d1 = d0 + SWEEP_TILE;
+    if (d1 > total_items) d1 = total_items;
+    const int32_t k0 = static_cast<int32_t>(d0 - c0), k1 = static_cast<int32_t>(d1 - c1);
+    const int nc = c1 - c0, nk = k1 - k0;
+    const int a_last = (c1 + 1 <= ncol) ? c1 + 1 : ncol;  // p index
+    for (int j = threadIdx.x; c0 + j <= a_last; j += BP_THREADS) as[j] = gp[c0 + j];
+    for (int j = threadIdx.x; j <= nk; j += BP_THREADS) {
+      const int32_t k = k0 - 1 + j;
+      is[j] = (k >= 0 && k < nnz) ? ptx::ld_stream_s32(gi + k) : 0;
+    }
+    __syncthreads();
+
+    const int items = nc + nk;
+    int d_lo = threadIdx.x * BP_IPT;
+    if (d_lo > items) d_lo = items;
+    int d_hi = d_lo + BP_IPT;
+    if (d_hi > items) d_hi = items;
+    if (d_lo >= d_hi) continue;
+    // column ends consumed before d_lo: end of column c0+j is as[j+1]
+    int lo = d_lo > nk ? d_lo - nk : 0;
+    int hi = d_lo < nc ? d_lo : nc;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (as[mid + 1] - k0 <= d_lo - mid - 1)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    int ci = lo;
+    int ki = d_lo - ci;             // relative to k0; entry k0+ki is is[ki+1]
+    int col_end = as[ci + 1] - k0;  // relative end of column c0+ci (stale past the last column: no items remain)
+    // band of the previous entry when I start inside a column
+    int cur = 0;
+    if (k0 + ki > as[ci]) {  // column c0+ci started before my first item
+      const int32_t prev_row = is[ki];
+      int blo = 0, bhi = nb;  // largest b with rbs[b] <= prev_row
+      while (blo < bhi) {
+        const int mid = (blo + bhi + 1) >> 1;
+        if (rbs[mid] <= prev_row)
+          blo = mid;
+        else
+          bhi = mid - 1;
+      }
+      cur = blo;
+    }
+    int32_t next_rb = rbs[cur + 1];  // cur <= nb-1 always (rows < nrow = rbs[nb])
+    for (int it = d_lo; it < d_hi; ++it) {
+      const int64_t c = c0 + ci;
+      if (ki < col_end) {
+        const int32_t row = is[ki + 1];
+        while (row >= next_rb) {  // entering band cur+1 (possibly skipping empty bands)
+          ++cur;
+          bpt[static_cast<int64_t>(cur - 1) * ncol + c] = k0 + ki;
+          next_rb = rbs[cur + 1];
+        }
+        ++ki;
+      } else {
+        const int32_t e = k0 + col_end;
+        while (cur < nb - 1) {  // bands after the column's last entry start at its end
+          ++cur;
+          bpt[static_cast<int64_t>(cur - 1) * ncol + c] = e;
+        }
+        cur = 0;
+        next_rb = rbs[1];
+        ++ci;
+        col_end = as[ci + 1] - k0;
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// shared skeleton of the band kernels
+// ================================================================================================
+constexpr int BAND_THREADS = 512;
+constexpr int BAND_WARPS = BAND_THREADS / 32;
+constexpr int BAND_CH = BAND_THREADS;  // columns per chunk: 32 per warp, one run descriptor per lane
+
+struct BandView {
+  const int32_t* i;
+  const int32_t* p;
+  const double* x;
+  int32_t ncol;
+  int nb;
+  int S;
+  const int32_t* rb;   // [nb+1]
+  const int32_t* cs;   // [S+1]
+  const int32_t* bpt;  // [(nb-1)*ncol]
+};
+
+__device__ __forceinline__ int32_t band_start(const BandView& a, int b, int64_t c) {
+  if (b == 0) return __ldg(a.p + c);
+  if (b == a.nb) return __ldg(a.p + c + 1);
+  return __ldg(a.bpt + static_cast<int64_t>(b - 1) * a.ncol + c);
+}
+
+// One warp, 32 runs (start s, length len per lane).  The concatenated entries are walked 32*U at a
+// time in lane order = (run, position) order: for every group of U steps first load(k, l, valid) is
+// called U times (all loads of the group are in flight together — the kernels are latency-bound
+// otherwise), then use(payload) U times in step order.  k = entry index, l = lane owning the run.
+// Every lane calls load/use in every step (valid = false past the end), so they may use warp-wide
+// primitives.
+template <int U, typename Payload, typename Load, typename Use>
+__device__ __forceinline__ void warp_walk_runs(int32_t s, int32_t len, int lane, Load load, Use use) {
+  int32_t incl = len;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int32_t up = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += up;
+  }
+  const int32_t excl = incl - len;
+  const int32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  for (int32_t base = 0; base < total; base += 32 * U) {
+    Payload pl[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int32_t q = base + u * 32 + lane;
+      int l = 0;  // largest l with excl[l] <= q (skips empty runs)
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int cand = l + step;
+        const int32_t e = __shfl_sync(0xffffffffu, excl, cand & 31);
+        if (cand < 32 && e <= q) l = cand;
+      }
+      const int32_t rs = __shfl_sync(0xffffffffu, s, l);
+      const int32_t re = __shfl_sync(0xffffffffu, excl, l);
+      pl[u] = load(rs + (q - re), l, q < total);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + u * 32 < total) use(pl[u]);  // warp-uniform
+    }
+  }
+}
+
+// ================================================================================================
+// row-indexed sums: rowSums / rowMeans / A v
+// ================================================================================================
+constexpr int BAND_UNROLL = 4;
+
+struct ScatterItem {
+  int32_t r;
+  double xv, w;
+};
+
+struct ScatterArgs {
+  BandView bv;
+  const double* v;  // [ncol] or null (rowSums)
+  double* out;      // [nrow]; pre-zeroed when S > 1
+};
+
+template <bool SPMV>
+__global__ void __launch_bounds__(BAND_THREADS) band_scatter_kernel(const ScatterArgs a) {
+  extern __shared__ double acc[];
+  const BandView& bv = a.bv;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int units = bv.nb * bv.S;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int h = u / bv.nb, b = u % bv.nb;  // consecutive CTAs = consecutive bands of one split
+    const int32_t row0 = bv.rb[b];
+    const int32_t R = bv.rb[b + 1] - row0;
+    if (R <= 0) continue;
+    const int32_t c_lo = bv.cs[h], c_hi = bv.cs[h + 1];
+    __syncthreads();
+    for (int r = tid; r < R; r += BAND_THREADS) acc[r] = 0.0;
+    __syncthreads();
+    // software-pipelined descriptors: the next chunk's are fetched (and its runs prefetched to L2)
+    // while the current chunk is walked
+    int32_t ns = 0, ne = 0;
+    double nv = 0.0;
+    {
+      const int64_t c = static_cast<int64_t>(c_lo) + tid;
+      if (c < c_hi) {
+        ns = band_start(bv, b, c);
+        ne = band_start(bv, b + 1, c);
+        if (SPMV) nv = __ldg(a.v + c);
+      }
+    }
+    for (int64_t cbase = c_lo; cbase < c_hi; cbase += BAND_CH) {
+      const int32_t s = ns, e = ne;
+      const double vc = nv;
+      ns = ne = 0;
+      nv = 0.0;
+      {
+        const int64_t c = cbase + BAND_CH + tid;
+        if (c < c_hi) {
+          ns = band_start(bv, b, c);
+          ne = band_start(bv, b + 1, c);
+          if (SPMV) nv = __ldg(a.v + c);
+          for (int32_t k = ns & ~31; k < ne; k += 32) ptx::prefetch_l2(bv.i + k);
+          for (int32_t k = ns & ~15; k < ne; k += 16) ptx::prefetch_l2(bv.x + k);
+        }
+      }
+      warp_walk_runs<BAND_UNROLL, ScatterItem>(
+          s, e - s, lane,
+          [&](int32_t k, int l, bool valid) {
+            ScatterItem it;
+            it.r = -1;
+            it.xv = 0.0;
+            it.w = 1.0;
+            if (SPMV) it.w = __shfl_sync(0xffffffffu, vc, l);
+            if (valid) {
+              it.r = ptx::ld_stream_s32(bv.i + k) - row0;
+              it.xv = ptx::ld_stream_f64(bv.x + k);
+            }
+            return it;
+          },
+          [&](const ScatterItem& it) {
+            if (it.r >= 0) atomicAdd(&acc[it.r], SPMV ? __dmul_rn(it.xv, it.w) : it.xv);
+          });
+    }
+    __syncthreads();
+    if (bv.S == 1) {
+      for (int r = tid; r < R; r += BAND_THREADS) a.out[row0 + r] = acc[r];
+    } else {
+      for (int r = tid; r < R; r += BAND_THREADS) ptx::red_add_f64(a.out + row0 + r, acc[r]);
+    }
+  }
+}
+
+// ================================================================================================
+// transpose: banded stable scatter
+// ================================================================================================
+struct PlaceItem {
+  int32_t r, col;
+  double xv;
+};
+
+struct TransposeArgs {
+  BandView bv;
+  const int32_t* off;  // [nrow*S (+1)] first output slot of (row r, split h): off[r*S + h]
+  int32_t* i_out;
+  double* x_out;
+  int max_rows;  // R capacity of the shared-memory tables (even)
+};
+
+static size_t transpose_smem_bytes(int max_rows) {
+  const size_t R = static_cast<size_t>(max_rows);
+  return R * 4 * 2 /* cursor, rowpos */ + R * 2 * BAND_WARPS * 2 /* cnt, rel (u16) */ + 32;
+}
+
+__global__ void __launch_bounds__(BAND_THREADS) band_transpose_kernel(const TransposeArgs a) {
+  extern __shared__ __align__(16) unsigned char tsm[];
+  const BandView& bv = a.bv;
+  const int MR = a.max_rows;
+  uint32_t* cursor = reinterpret_cast<uint32_t*>(tsm);                      // [MR] next free slot of each row
+  uint32_t* rowpos = cursor + MR;                                           // [MR] slot base of the row for this chunk
+  uint32_t* cntw = rowpos + MR;                                             // [WARPS*MR/2] u16 pairs: entries of (warp, row)
+  uint16_t* rel = reinterpret_cast<uint16_t*>(cntw + (BAND_WARPS * MR) / 2);  // [WARPS*MR] running offset of (warp, row)
+  uint16_t* cnt16 = reinterpret_cast<uint16_t*>(cntw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int units = bv.nb * bv.S;
+
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int h = u / bv.nb, b = u % bv.nb;
+    const int32_t row0 = bv.rb[b];
+    const int32_t R = bv.rb[b + 1] - row0;
+    if (R <= 0) continue;
+    const int32_t c_lo = bv.cs[h], c_hi = bv.cs[h + 1];
+    __syncthreads();
+    for (int r = tid; r < R; r += BAND_THREADS)
+      cursor[r] = static_cast<uint32_t>(a.off[static_cast<int64_t>(row0 + r) * bv.S + h]);
+    for (int e = tid; e < (BAND_WARPS * MR) / 2; e += BAND_THREADS) cntw[e] = 0u;
+    __syncthreads();
+
+    int32_t ns = 0, ne = 0;
+    {
+      const int64_t c = static_cast<int64_t>(c_lo) + tid;
+      if (c < c_hi) {
+        ns = band_start(bv, b, c);
+        ne = band_start(bv, b + 1, c);
+      }
+    }
+    for (int64_t cbase = c_lo; cbase < c_hi; cbase += BAND_CH) {
+      const int32_t s = ns, e = ne;
+      ns = ne = 0;
+      {
+        const int64_t c = cbase + BAND_CH + tid;
+        if (c < c_hi) {
+          ns = band_start(bv, b, c);
+          ne = band_start(bv, b + 1, c);
+          for (int32_t k = ns & ~31; k < ne; k += 32) ptx::prefetch_l2(bv.i + k);
+          for (int32_t k = ns & ~15; k < ne; k += 16) ptx::prefetch_l2(bv.x + k);
+        }
+      }
+      // ---- pass 1: entries per (warp, row) of this chunk (order-free) -------------------------------
+      warp_walk_runs<BAND_UNROLL, int32_t>(
+          s, e - s, lane, [&](int32_t k, int l, bool valid) { return valid ? __ldg(bv.i + k) - row0 : -1; },
+          [&](const int32_t& r) {
+            if (r >= 0) {
+              const int idx = warp * MR + r;
+              atomicAdd(&cntw[idx >> 1], 1u << ((idx & 1) * 16));
+            }
+          });
+      __syncthreads();
+      // ---- per row: slot ranges of the 16 warps in warp (= column) order; advance the cursor ------------
+      for (int r = tid; r < R; r += BAND_THREADS) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < BAND_WARPS; ++w) {
+          const uint32_t c = cnt16[w * MR + r];
+          rel[w * MR + r] = static_cast<uint16_t>(run);
+          cnt16[w * MR + r] = 0;
+          run += c;
+        }
+        const uint32_t base = cursor[r];
+        rowpos[r] = base;
+        cursor[r] = base + run;
+      }
+      __syncthreads();
+      // ---- pass 2: place.  Equal rows inside a step are ranked in lane order = source column order ------
+      warp_walk_runs<BAND_UNROLL, PlaceItem>(
+          s, e - s, lane,
+          [&](int32_t k, int l, bool valid) {
+            PlaceItem it;
+            it.r = -1 - lane;  // unique sentinel: never matches another lane
+            it.col = static_cast<int32_t>(cbase + 32 * warp + l);
+            it.xv = 0.0;
+            if (valid) {
+              it.r = __ldg(bv.i + k) - row0;
+              it.xv = ptx::ld_stream_f64(bv.x + k);
+            }
+            return it;
+          },
+          [&](const PlaceItem& it) {
+            const unsigned same = __match_any_sync(0xffffffffu, it.r);
+            if (it.r >= 0) {
+              const int idx = warp * MR + it.r;
+              const uint32_t my = rel[idx];
+              const uint32_t pos = rowpos[it.r] + my + __popc(same & lt_mask);
+              a.i_out[pos] = it.col;
+              a.x_out[pos] = it.xv;
+              if ((same >> lane) == 1u) rel[idx] = static_cast<uint16_t>(my + __popc(same));  // highest lane of the group
+            }
+            __syncwarp();
+          });
+    }
+  }
+}
+
+__global__ void zero_i32_kernel(int32_t* d, int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride) d[k] = 0;
+}
+
+struct PhaseTrace {  // SB200_TRACE=1: per-phase device time on stderr
+  bool on;
+  cudaStream_t st;
+  cudaEvent_t ev[10];
+  const char* name[10];
+  int n = 0;
+  explicit PhaseTrace(cudaStream_t s) : on(getenv("SB200_TRACE") != nullptr), st(s) {}
+  void mark(const char* what) {
+    if (!on || n >= 10) return;
+    cudaEventCreate(&ev[n]);
+    cudaEventRecord(ev[n], st);
+    name[n++] = what;
+  }
+  void report(const char* title, const BandPlan* bp);
+};
+
+}  // namespace
+
+// ================================================================================================
+// the plan
+// ================================================================================================
+struct BandPlan {
+  int nb = 0, S = 0, max_rows = 0;
+  bool has_offsets = false;
+  int32_t* d_rb = nullptr;
+  int32_t* d_cs = nullptr;
+  int32_t* d_bpt = nullptr;
+  int32_t* d_rowptr = nullptr;  // [nrow+1]
+  int32_t* d_off = nullptr;     // [nrow*S+1] scan over (row, split); == d_rowptr when S == 1
+};
+
+namespace {
+void PhaseTrace::report(const char* title, const BandPlan* bp) {
+  if (!on) return;
+  cudaStreamSynchronize(st);
+  fprintf(stderr, "[sb200 trace] %s nb=%d S=%d maxrows=%d:", title, bp ? bp->nb : 0, bp ? bp->S : 0, bp ? bp->max_rows : 0);
+  for (int k = 1; k < n; ++k) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev[k - 1], ev[k]);
+    fprintf(stderr, " %s %.3f ms;", name[k], ms);
+  }
+  fprintf(stderr, "\n");
+  for (int k = 0; k < n; ++k) cudaEventDestroy(ev[k]);
+}
+}  // namespace
+
+void free_band_plan(BandPlan* bp, cudaStream_t s) {
+  if (!bp) return;
+  pool_free(bp->d_rb, s);
+  pool_free(bp->d_cs, s);
+  pool_free(bp->d_bpt, s);
+  if (bp->d_off != bp->d_rowptr) pool_free(bp->d_off, s);
+  pool_free(bp->d_rowptr, s);
+  delete bp;
+}
+
+// rows_cap: most rows a band may hold (consumer's shared-memory budget); want_bands: preferred band
+// count; S: column splits.  nnz > 0 and nrow > 0 required.
+static int build_band_plan(sb200_matrix* m, int rows_cap, int want_bands, int S, BandPlan** out) {
+  cudaStream_t st = m->stream;
+  const int32_t nrow = m->nrow, ncol = m->ncol;
+  const int64_t nnz = m->nnz;
+  BandPlan* bp = new (std::nothrow) BandPlan();
+  if (!bp) return fail(SB200_E_NOMEM, "host allocation failed");
+  struct Guard {
+    BandPlan*& p;
+    cudaStream_t s;
+    bool armed = true;
+    ~Guard() {
+      if (armed) free_band_plan(p, s);
+    }
+  } guard{bp, st};
+  PhaseTrace tr(st);
+  tr.mark("start");
+
+  // ---- geometry: enough bands that none exceeds rows_cap, not more than leaves ~3 entries per run ----
+  const double cap = 0.9 * rows_cap;
+  int nb = want_bands;
+  const int64_t floor_rows = static_cast<int64_t>((nrow + cap - 1) / cap);
+  const int64_t by_density = nnz / (static_cast<int64_t>(ncol > 0 ? ncol : 1) * 3);
+  if (nb > by_density) nb = static_cast<int>(by_density);
+  if (nb < floor_rows) nb = static_cast<int>(floor_rows);
+  if (nb < 1) nb = 1;
+  if (const char* e = getenv("SB200_BANDS")) {
+    const int v = atoi(e);
+    if (v >= floor_rows) nb = v;
+  }
+  double eps = static_cast<double>(nrow) / (static_cast<double>(nb) * cap);
+  if (eps < 1e-3) eps = 1e-3;
+  if (eps > 1.0) eps = 1.0;
+  if (S < 1) S = 1;
+  if (S > ncol) S = ncol > 0 ? ncol : 1;
+  bp->nb = nb;
+  bp->S = S;
+
+  const int64_t scan_n = static_cast<int64_t>(nrow) * S;
+  if (scan_n > 2000000000LL) return fail(SB200_E_UNSUPPORTED, "band plan: nrow * splits too large");
+  uint32_t* d_cnt = nullptr;
+  void* d_scan_ws = nullptr;
+  int32_t* d_maxrows = nullptr;
+  const size_t scan_ws = scan_workspace_bytes(scan_n);
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&d_cnt), sizeof(uint32_t) * static_cast<size_t>(scan_n), st));
+  struct Tmp {
+    void* p[3];
+    cudaStream_t s;
+    ~Tmp() {
+      for (void* q : p) pool_free(q, s);
+    }
+  } tmp{{d_cnt, nullptr, nullptr}, st};
+  SB_TRY(pool_alloc(&d_scan_ws, scan_ws, st));
+  tmp.p[1] = d_scan_ws;
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&d_maxrows), sizeof(int32_t), st));
+  tmp.p[2] = d_maxrows;
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&bp->d_cs), sizeof(int32_t) * (S + 1), st));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&bp->d_rb), sizeof(int32_t) * (nb + 1), st));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&bp->d_off), sizeof(int32_t) * static_cast<size_t>(scan_n + 1), st));
+  if (S == 1) {
+    bp->d_rowptr = bp->d_off;
+  } else {
+    SB_TRY(pool_alloc(reinterpret_cast<void**>(&bp->d_rowptr), sizeof(int32_t) * (static_cast<size_t>(nrow) + 1), st));
+  }
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&bp->d_bpt),
+                    sizeof(int32_t) * static_cast<size_t>(nb > 1 ? nb - 1 : 1) * static_cast<size_t>(ncol > 0 ? ncol : 1), st));
+
+  // ---- P1 --------------------------------------------------------------------------------------------
+  split_bounds_kernel<<<(S + 1 + 63) / 64, 64, 0, st>>>(m->d_p, ncol, nnz, S, bp->d_cs);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  SB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * static_cast<size_t>(scan_n), st));
+  {
+    int per_split = (m->sm_count + S - 1) / S;
+    const int64_t by_work = (nnz / S) / (HIST_THREADS * 16) + 1;
+    if (per_split > by_work) per_split = static_cast<int>(by_work);
+    if (per_split < 1) per_split = 1;
+    if (nrow <= HIST_SMEM_MAX_WORDS) {
+      const size_t smem = sizeof(uint32_t) * static_cast<size_t>(nrow);
+      SB_CUDA(cudaFuncSetAttribute(row_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      row_hist_kernel<true><<<S * per_split, HIST_THREADS, smem, st>>>(m->d_i, m->d_p, bp->d_cs, S, per_split, nrow, d_cnt);
+    } else {
+      per_split *= 4;
+      row_hist_kernel<false><<<S * per_split, HIST_THREADS, 0, st>>>(m->d_i, m->d_p, bp->d_cs, S, per_split, nrow, d_cnt);
+    }
+    count_launch();
+    SB_CUDA(cudaGetLastError());
+  }
+  tr.mark("hist");
+  SB_TRY(exclusive_scan_u32(st, d_cnt, bp->d_off, scan_n, nullptr, d_scan_ws, scan_ws));
+  if (S > 1) {
+    int64_t blocks = (static_cast<int64_t>(nrow) + 1 + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    extract_rowptr_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(bp->d_off, nrow, S, bp->d_rowptr);
+    count_launch();
+    SB_CUDA(cudaGetLastError());
+  }
+  bp->has_offsets = true;
+  tr.mark("scan");
+  // ---- P2 ---------------------------------------------------------------------------------------------
+  band_bounds_kernel<<<(nb + 1 + 127) / 128, 128, 0, st>>>(bp->d_rowptr, nrow, nnz, nb, eps, bp->d_rb);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  SB_CUDA(cudaMemsetAsync(d_maxrows, 0, sizeof(int32_t), st));
+  band_max_rows_kernel<<<1, 256, 0, st>>>(bp->d_rb, nb, d_maxrows);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  int32_t h_maxrows = 0;
+  SB_CUDA(cudaMemcpyAsync(&h_maxrows, d_maxrows, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  tr.mark("bands");
+  // ---- P3 ---------------------------------------------------------------------------------------------
+  if (nb > 1) {
+    const size_t smem = sizeof(int32_t) * (2 * (SWEEP_TILE + 4) + static_cast<size_t>(nb) + 1);
+    SB_CUDA(cudaFuncSetAttribute(band_ptr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int64_t blocks = m->n_tiles;
+    const int64_t capb = static_cast<int64_t>(m->sm_count) * 6;
+    if (blocks > capb) blocks = capb;
+    band_ptr_kernel<<<static_cast<unsigned>(blocks), BP_THREADS, smem, st>>>(m->d_i, m->d_p, m->d_plan, m->n_tiles, ncol,
+                                                                            static_cast<int32_t>(nnz), bp->d_rb, nb, bp->d_bpt);
+    count_launch();
+    SB_CUDA(cudaGetLastError());
+  }
+  tr.mark("band ptrs");
+  SB_CUDA(cudaStreamSynchronize(st));
+  bp->max_rows = h_maxrows;
+  tr.report("band plan", bp);
+  if (h_maxrows > rows_cap) return fail(SB200_E_UNSUPPORTED, "band plan: a row band exceeds its shared-memory budget");
+  guard.armed = false;
+  *out = bp;
+  return SB200_OK;
+}
+
+static BandView make_view(const sb200_matrix* m, const BandPlan* bp) {
+  BandView v;
+  v.i = m->d_i;
+  v.p = m->d_p;
+  v.x = m->d_x;
+  v.ncol = m->ncol;
+  v.nb = bp->nb;
+  v.S = bp->S;
+  v.rb = bp->d_rb;
+  v.cs = bp->d_cs;
+  v.bpt = bp->d_bpt;
+  return v;
+}
+
+// ---- row-indexed sums ----------------------------------------------------------------------------------
+constexpr int SCATTER_ROWS_CAP = 12288;  // 96 KB of FP64 accumulators: two CTAs per SM
+
+int ensure_scatter_plan(sb200_matrix* m) {
+  if (m->plan_scatter) return SB200_OK;
+  const int bands = m->sm_count;      // one band per SM ...
+  int S = 4;                          // ... times four column splits = two waves of two CTAs per SM
+  if (const char* e = getenv("SB200_SCATTER_SPLITS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 64) S = v;
+  }
+  return build_band_plan(m, SCATTER_ROWS_CAP, bands, S, &m->plan_scatter);
+}
+
+int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out) {
+  SB_TRY(ensure_scatter_plan(m));
+  const BandPlan* bp = m->plan_scatter;
+  ScatterArgs a;
+  a.bv = make_view(m, bp);
+  a.v = d_v;
+  a.out = d_out;
+  if (bp->S > 1) SB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * static_cast<size_t>(m->nrow), m->stream));
+  const size_t smem = sizeof(double) * static_cast<size_t>(bp->max_rows > 0 ? bp->max_rows : 1);
+  int ctas = static_cast<int>((200 * 1024) / (smem + 2048));
+  if (ctas > 2) ctas = 2;
+  if (ctas < 1) ctas = 1;
+  int grid = m->sm_count * ctas;
+  if (grid > bp->nb * bp->S) grid = bp->nb * bp->S;
+  if (d_v) {
+    SB_CUDA(cudaFuncSetAttribute(band_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    band_scatter_kernel<true><<<grid, BAND_THREADS, smem, m->stream>>>(a);
+  } else {
+    SB_CUDA(cudaFuncSetAttribute(band_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    band_scatter_kernel<false><<<grid, BAND_THREADS, smem, m->stream>>>(a);
+  }
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return SB200_OK;
+}
+
+// ---- transpose -------------------------------------------------------------------------------------------
+constexpr int TRANSPOSE_ROWS_CAP = 2688;  // 72 B of tables per row: one CTA per SM at the cap, two below half
+
+int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double* d_x_out) {
+  cudaStream_t st = m->stream;
+  const int32_t nrow = m->nrow;
+  const int64_t nnz = m->nnz;
+  if (nnz == 0 || nrow == 0) {
+    int64_t blocks = (static_cast<int64_t>(nrow) + 1 + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    zero_i32_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(d_p_out, static_cast<int64_t>(nrow) + 1);
+    count_launch();
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+  }
+  int S = 2, bands = m->sm_count;
+  if (const char* e = getenv("SB200_TRANSPOSE_SPLITS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 64) S = v;
+  }
+  if (const char* e = getenv("SB200_TRANSPOSE_BANDS")) {
+    const int v = atoi(e);
+    if (v >= 1) bands = v;
+  }
+  BandPlan* bp = nullptr;
+  SB_TRY(build_band_plan(m, TRANSPOSE_ROWS_CAP, bands, S, &bp));
+  PhaseTrace tr(st);
+  tr.mark("start");
+  int rc = SB200_OK;
+  cudaError_t e = cudaMemcpyAsync(d_p_out, bp->d_rowptr, sizeof(int32_t) * (static_cast<size_t>(nrow) + 1),
+                                  cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) rc = cuda_fail(e, "copy of the new column pointers", __FILE__, __LINE__);
+  if (rc == SB200_OK) {
+    TransposeArgs a;
+    a.bv = make_view(m, bp);
+    a.off = bp->d_off;
+    a.i_out = d_i_out;
+    a.x_out = d_x_out;
+    a.max_rows = (bp->max_rows + 1) & ~1;
+    const size_t smem = transpose_smem_bytes(a.max_rows);
+    int ctas = smem <= 100 * 1024 ? 2 : 1;
+    int grid = m->sm_count * ctas;
+    if (grid > bp->nb * bp->S) grid = bp->nb * bp->S;
+    e = cudaFuncSetAttribute(band_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) {
+      band_transpose_kernel<<<grid, BAND_THREADS, smem, st>>>(a);
+      count_launch();
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) rc = cuda_fail(e, "band_transpose_kernel", __FILE__, __LINE__);
+  }
+  tr.mark("scatter");
+  tr.report("transpose", bp);
+  free_band_plan(bp, st);  // stream-ordered: released after the kernel
+  return rc;
+}
+
+void free_matrix_plans(sb200_matrix* m, cudaStream_t s) {
+  if (m->plan_scatter) {
+    free_band_plan(m->plan_scatter, s);
+    m->plan_scatter = nullptr;
+  }
+}
+
+}  // namespace sb200

@@ -31,6 +31,34 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 size_t padded_bytes(size_t bytes) { return ((bytes + 15) / 16) * 16 + 16; }
 
+// Stream-ordered allocation from the device's default memory pool, with the pool told to keep
+// freed memory (release threshold = max): after the first use of a size class an allocation is
+// a pool lookup, not a driver call — a multi-GB cudaMalloc/cudaFree pair costs milliseconds,
+// comparable to the sweeps themselves.
+int pool_alloc(void** out, size_t bytes, cudaStream_t s) {
+  static std::atomic<unsigned> configured{0};
+  int dev = 0;
+  SB_CUDA(cudaGetDevice(&dev));
+  if (dev < 32 && !(configured.load() & (1u << dev))) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    configured.fetch_or(1u << dev);
+  }
+  cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, s);
+  if (e != cudaSuccess) {
+    *out = nullptr;
+    return cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+  }
+  return SB200_OK;
+}
+void pool_free(void* ptr, cudaStream_t s) {
+  if (ptr) cudaFreeAsync(ptr, s);
+}
+
 static int require_device(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -44,16 +72,23 @@ static int require_device(int device) {
 
 static void free_matrix(sb200_matrix* m) {
   if (!m) return;
+  // frees are ordered after the handle's own work; a caller-owned stream may be gone already
+  cudaStream_t fs = m->owns_stream ? m->stream : static_cast<cudaStream_t>(0);
+  if (!m->owns_stream && m->stream) cudaStreamSynchronize(m->stream), cudaGetLastError();
   if (m->owns_arrays) {
-    cudaFree(m->d_i);
-    cudaFree(m->d_p);
-    cudaFree(m->d_x);
+    pool_free(m->d_i, fs);
+    pool_free(m->d_p, fs);
+    pool_free(m->d_x, fs);
   }
-  cudaFree(m->d_plan);
-  cudaFree(m->d_ws);
-  cudaFree(m->d_stage_in);
-  cudaFree(m->d_stage_out);
-  if (m->owns_stream && m->stream) cudaStreamDestroy(m->stream);
+  free_matrix_plans(m, fs);
+  pool_free(m->d_plan, fs);
+  pool_free(m->d_ws, fs);
+  pool_free(m->d_stage_in, fs);
+  pool_free(m->d_stage_out, fs);
+  if (m->owns_stream && m->stream) {
+    cudaStreamSynchronize(m->stream);
+    cudaStreamDestroy(m->stream);
+  }
   m->magic = 0;
   delete m;
 }
@@ -91,12 +126,14 @@ int alloc_matrix(int device, int32_t nrow, int32_t ncol, int64_t nnz, sb200_matr
   sb200_matrix* m = nullptr;
   SB_TRY(new_handle(device, nrow, ncol, nnz, &m));
   m->owns_arrays = true;
-  cudaError_t e = cudaMalloc(&m->d_i, padded_bytes(sizeof(int32_t) * static_cast<size_t>(nnz)));
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_p, padded_bytes(sizeof(int32_t) * (static_cast<size_t>(ncol) + 1)));
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_x, padded_bytes(sizeof(double) * static_cast<size_t>(nnz)));
-  if (e != cudaSuccess) {
+  int rc = pool_alloc(reinterpret_cast<void**>(&m->d_i), padded_bytes(sizeof(int32_t) * static_cast<size_t>(nnz)), m->stream);
+  if (rc == SB200_OK)
+    rc = pool_alloc(reinterpret_cast<void**>(&m->d_p), padded_bytes(sizeof(int32_t) * (static_cast<size_t>(ncol) + 1)), m->stream);
+  if (rc == SB200_OK)
+    rc = pool_alloc(reinterpret_cast<void**>(&m->d_x), padded_bytes(sizeof(double) * static_cast<size_t>(nnz)), m->stream);
+  if (rc != SB200_OK) {
     free_matrix(m);
-    return cuda_fail(e, "cudaMalloc(mirror arrays)", __FILE__, __LINE__);
+    return rc;
   }
   *out = m;
   return SB200_OK;
@@ -104,12 +141,12 @@ int alloc_matrix(int device, int32_t nrow, int32_t ncol, int64_t nnz, sb200_matr
 
 int finish_matrix(sb200_matrix* m, unsigned flags) {
   m->ws_bytes = 16 + 4 * 1024 + 8 * 1024 + 64;
-  SB_CUDA(cudaMalloc(&m->d_ws, m->ws_bytes));
+  SB_TRY(pool_alloc(&m->d_ws, m->ws_bytes, m->stream));
   SB_CUDA(cudaMemsetAsync(m->d_ws, 0, m->ws_bytes, m->stream));
   m->stage_len = (m->nrow > m->ncol ? m->nrow : m->ncol);
   if (m->stage_len < 1) m->stage_len = 1;
-  SB_CUDA(cudaMalloc(&m->d_stage_in, padded_bytes(sizeof(double) * static_cast<size_t>(m->stage_len))));
-  SB_CUDA(cudaMalloc(&m->d_stage_out, padded_bytes(sizeof(double) * static_cast<size_t>(m->stage_len))));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&m->d_stage_in), padded_bytes(sizeof(double) * static_cast<size_t>(m->stage_len)), m->stream));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&m->d_stage_out), padded_bytes(sizeof(double) * static_cast<size_t>(m->stage_len)), m->stream));
   if (!(flags & SB200_NO_VALIDATE)) SB_TRY(validate_structure(m));
   SB_TRY(build_sweep_plan(m));
   SB_CUDA(cudaStreamSynchronize(m->stream));

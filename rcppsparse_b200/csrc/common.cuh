@@ -37,9 +37,9 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 // geometry of the merge-path sweep (sweep.cu) — one "item" is either one stored entry or one
 // column end; a tile is SWEEP_TILE consecutive items on the merge path of (p[1..ncol], 0..nnz).
 // ---------------------------------------------------------------------------------------------
-constexpr int SWEEP_THREADS = 512;
-constexpr int SWEEP_IPT = 7;  // odd => conflict-free 8-byte shared-memory reads at stride IPT
-constexpr int SWEEP_TILE = SWEEP_THREADS * SWEEP_IPT;  // 3584 items
+constexpr int SWEEP_THREADS = 256;
+constexpr int SWEEP_IPT = 15;  // odd => conflict-free 8-byte shared-memory reads at stride IPT
+constexpr int SWEEP_TILE = SWEEP_THREADS * SWEEP_IPT;  // 3840 items
 
 constexpr int NUM_SMS_B200 = 148;
 
@@ -74,6 +74,8 @@ struct sb200_matrix {
   double* d_stage_in;
   double* d_stage_out;
   int64_t stage_len;
+  // row-band plan for the row-indexed sweeps (bands.cu); structure-only, built on first use
+  sb200::BandPlan* plan_scatter;
 };
 
 namespace sb200 {
@@ -113,12 +115,17 @@ size_t scan_workspace_bytes(int64_t n);
 int exclusive_scan_u32(cudaStream_t s, const uint32_t* d_in, int32_t* d_out, int64_t n, unsigned long long* d_total,
                        void* d_ws, size_t ws_bytes);
 
-// transpose.cu
+// bands.cu
 int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double* d_x_out);
+int ensure_scatter_plan(sb200_matrix* m);
+int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out);  // d_v null = rowSums
+void free_matrix_plans(sb200_matrix* m, cudaStream_t s);
 
 // mirror.cu
 int alloc_matrix(int device, int32_t nrow, int32_t ncol, int64_t nnz, sb200_matrix** out);  // owns arrays, uninitialised
 int finish_matrix(sb200_matrix* m, unsigned flags);  // validate + plan + workspace
 size_t padded_bytes(size_t bytes);
+int pool_alloc(void** out, size_t bytes, cudaStream_t s);  // stream-ordered, from a retaining pool
+void pool_free(void* ptr, cudaStream_t s);
 
 }  // namespace sb200

@@ -72,7 +72,6 @@ struct SweepParams {
   int32_t nnz;
   const double* v;
   double* out;
-  double divisor;      // 0 = none
   int32_t* carry_col;  // [grid]
   double* carry_val;   // [grid]
   unsigned int* ticket;
@@ -89,9 +88,8 @@ struct StageMeta {
   int32_t pad;
 };
 
-template <int THREADS>
 struct SweepGeom {
-  static constexpr int TILE = THREADS * SWEEP_IPT;
+  static constexpr int TILE = SWEEP_TILE;
   static constexpr int X_ELEMS = TILE + 2;   // +1 align-down slack, +1 round-up
   static constexpr int A_ELEMS = TILE + 8;   // nc+1 values, +3 align-down, +3 round-up, +1 spare
   static constexpr int I_ELEMS = TILE + 8;
@@ -101,22 +99,28 @@ struct SweepGeom {
   static constexpr size_t stage_bytes(bool with_i) { return X_BYTES + A_BYTES + (with_i ? I_BYTES : 0); }
 };
 
-__device__ __forceinline__ double finalize(double s, double divisor) { return divisor != 0.0 ? s / divisor : s; }
+constexpr int SWEEP_BLOCK = SWEEP_THREADS + 32;  // 8 consumer warps + 1 producer warp
 
-template <int MODE, int THREADS, int STAGES>
-__global__ void __launch_bounds__(THREADS) sweep_kernel(const SweepParams prm) {
-  using G = SweepGeom<THREADS>;
+// consumer-only barrier (the producer warp never joins it)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SWEEP_THREADS) : "memory"); }
+
+template <int MODE, int STAGES>
+__global__ void __launch_bounds__(SWEEP_BLOCK) sweep_kernel(const SweepParams prm) {
+  using G = SweepGeom;
+  constexpr int THREADS = SWEEP_THREADS;
   constexpr int TILE = G::TILE;
   constexpr int IPT = SWEEP_IPT;
   constexpr bool WITH_I = (MODE == SWEEP_SPMV_T || MODE == SWEEP_SPMV);
   constexpr bool REDUCES = (MODE == SWEEP_COLSUM || MODE == SWEEP_SPMV_T);
   constexpr int WARPS = THREADS / 32;
+  static_assert(WARPS <= 32, "warp fold uses one lane per warp");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t full_bar[STAGES];   // producer -> consumers: the stage's bytes have landed
+  __shared__ uint64_t empty_bar[STAGES];  // consumers -> producer: every consumer warp is done with the stage
   __shared__ StageMeta meta[STAGES];
-  __shared__ double warp_sum[WARPS];
-  __shared__ int warp_flag[WARPS];
+  __shared__ double warp_sum[2][WARPS];   // double-buffered by tile parity: one barrier per tile
+  __shared__ int warp_flag[2][WARPS];
   __shared__ int cta_info[4];
 
   const int tid = threadIdx.x;
@@ -137,73 +141,71 @@ __global__ void __launch_bounds__(THREADS) sweep_kernel(const SweepParams prm) {
     return reinterpret_cast<int32_t*>(smem_raw + s * G::stage_bytes(WITH_I) + G::X_BYTES + G::A_BYTES);
   };
 
-  // ---- producer state (thread 0 only) --------------------------------------------------------
-  int32_t pl_lo = 0, pl_hi = 0;  // plan[t_issue], plan[t_issue + 1]
-  int64_t t_issue = t_begin;
-  auto issue = [&](int s) {
-    // called by thread 0 with t_issue < t_end; stage s is free
-    const int64_t d0 = t_issue * TILE;
-    int64_t d1 = d0 + TILE;
-    if (d1 > total_items) d1 = total_items;
-    const int32_t c0 = pl_lo, c1 = pl_hi;
-    const int32_t k0 = static_cast<int32_t>(d0 - c0), k1 = static_cast<int32_t>(d1 - c1);
-    StageMeta mt;
-    mt.c0 = c0;
-    mt.nc = c1 - c0;
-    mt.k0 = k0;
-    mt.nk = k1 - k0;
-    // column-end window: p[c0+1 .. min(c1+1, ncol)]
-    const int32_t a_first = c0 + 1;
-    const int32_t a_last = (c1 + 1 <= prm.ncol) ? c1 + 1 : prm.ncol;
-    const int32_t a_al = a_first & ~3;
-    const int32_t a_cnt = (a_last >= a_first) ? (((a_last - a_al + 1) + 3) & ~3) : 0;
-    mt.a_off = a_first - a_al;
-    const int32_t x_al = k0 & ~1;
-    const int32_t x_cnt = (mt.nk > 0) ? (((k1 - x_al) + 1) & ~1) : 0;
-    mt.x_off = k0 - x_al;
-    const int32_t i_al = k0 & ~3;
-    const int32_t i_cnt = (WITH_I && mt.nk > 0) ? (((k1 - i_al) + 3) & ~3) : 0;
-    mt.i_off = k0 - i_al;
-    mt.pad = 0;
-    meta[s] = mt;
-    const uint32_t bytes = static_cast<uint32_t>(a_cnt) * 4u + static_cast<uint32_t>(x_cnt) * 8u +
-                           static_cast<uint32_t>(i_cnt) * 4u;
-    ptx::mbar_arrive_expect_tx(&full_bar[s], bytes);
-    if (a_cnt > 0) ptx::bulk_g2s(stage_a(s), prm.p + a_al, static_cast<uint32_t>(a_cnt) * 4u, &full_bar[s]);
-    if (x_cnt > 0) ptx::bulk_g2s(stage_x(s), prm.x + x_al, static_cast<uint32_t>(x_cnt) * 8u, &full_bar[s]);
-    if (i_cnt > 0) ptx::bulk_g2s(stage_i(s), prm.i + i_al, static_cast<uint32_t>(i_cnt) * 4u, &full_bar[s]);
-    // roll the plan window forward; the load lands while the CTA works on earlier tiles
-    ++t_issue;
-    pl_lo = pl_hi;
-    if (t_issue < t_end) pl_hi = __ldg(prm.plan + t_issue + 1);
-  };
-
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full_bar[s], 1);
-    ptx::fence_mbar_init();
-    int split = 0;
-    if (n_local > 0) {
-      pl_lo = __ldg(prm.plan + t_begin);
-      pl_hi = __ldg(prm.plan + t_begin + 1);
-      // does this CTA start in the middle of a column?  (its first completed column then also
-      // owns partial sums carried by earlier CTAs and must be stored un-finalised)
-      const int64_t k_begin = t_begin * TILE - pl_lo;
-      if (blockIdx.x > 0 && pl_lo < prm.ncol && k_begin > __ldg(prm.p + pl_lo)) split = 1;
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], WARPS);
     }
-    cta_info[0] = split;
+    ptx::fence_mbar_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    for (int s = 0; s < STAGES && t_issue < t_end; ++s) issue(s);
-  }
-  const bool cta_split_start = cta_info[0] != 0;
 
-  double cta_carry = 0.0;     // partial sum of the column in progress, carried across this CTA's tiles
-  bool cta_seen_end = false;  // has any column ended inside this CTA yet?
+  if (warp == WARPS) {
+    // =========================== producer warp: one lane drives the TMA ring ===========================
+    if (lane == 0 && n_local > 0) {
+      int32_t pl_lo = __ldg(prm.plan + t_begin);      // plan[t], plan[t + 1] of the tile being issued
+      int32_t pl_hi = __ldg(prm.plan + t_begin + 1);
+      for (int j = 0; j < n_local; ++j) {
+        const int s = j % STAGES;
+        const int64_t t = t_begin + j;
+        // fetch the next plan entry before (possibly) blocking on the stage
+        int32_t pl_next = 0;
+        if (j + 1 < n_local) pl_next = __ldg(prm.plan + t + 2);
+        if (j >= STAGES) ptx::mbar_wait(&empty_bar[s], static_cast<uint32_t>(j / STAGES - 1) & 1u);
+        const int64_t d0 = t * TILE;
+        int64_t d1 = d0 + TILE;
+        if (d1 > total_items) d1 = total_items;
+        const int32_t c0 = pl_lo, c1 = pl_hi;
+        const int32_t k0 = static_cast<int32_t>(d0 - c0), k1 = static_cast<int32_t>(d1 - c1);
+        StageMeta mt;
+        mt.c0 = c0;
+        mt.nc = c1 - c0;
+        mt.k0 = k0;
+        mt.nk = k1 - k0;
+        // column-end window: p[c0+1 .. min(c1+1, ncol)]
+        const int32_t a_first = c0 + 1;
+        const int32_t a_last = (c1 + 1 <= prm.ncol) ? c1 + 1 : prm.ncol;
+        const int32_t a_al = a_first & ~3;
+        const int32_t a_cnt = (a_last >= a_first) ? (((a_last - a_al + 1) + 3) & ~3) : 0;
+        mt.a_off = a_first - a_al;
+        const int32_t x_al = k0 & ~1;
+        const int32_t x_cnt = (mt.nk > 0) ? (((k1 - x_al) + 1) & ~1) : 0;
+        mt.x_off = k0 - x_al;
+        const int32_t i_al = k0 & ~3;
+        const int32_t i_cnt = (WITH_I && mt.nk > 0) ? (((k1 - i_al) + 3) & ~3) : 0;
+        mt.i_off = k0 - i_al;
+        mt.pad = 0;
+        meta[s] = mt;
+        const uint32_t bytes = static_cast<uint32_t>(a_cnt) * 4u + static_cast<uint32_t>(x_cnt) * 8u +
+                               static_cast<uint32_t>(i_cnt) * 4u;
+        ptx::mbar_arrive_expect_tx(&full_bar[s], bytes);
+        if (a_cnt > 0) ptx::bulk_g2s(stage_a(s), prm.p + a_al, static_cast<uint32_t>(a_cnt) * 4u, &full_bar[s]);
+        if (x_cnt > 0) ptx::bulk_g2s(stage_x(s), prm.x + x_al, static_cast<uint32_t>(x_cnt) * 8u, &full_bar[s]);
+        if (i_cnt > 0) ptx::bulk_g2s(stage_i(s), prm.i + i_al, static_cast<uint32_t>(i_cnt) * 4u, &full_bar[s]);
+        pl_lo = pl_hi;
+        pl_hi = pl_next;
+      }
+    }
+    return;
+  }
+
+  // ======================================= consumer warps ================================================
+  double cta_carry = 0.0;  // partial sum of the column in progress, carried across this CTA's tiles
   int32_t last_c1 = 0, last_k1 = 0;
 
   for (int j = 0; j < n_local; ++j) {
     const int s = j % STAGES;
+    const int buf = j & 1;
     const uint32_t parity = static_cast<uint32_t>(j / STAGES) & 1u;
     ptx::mbar_wait(&full_bar[s], parity);
     const StageMeta mt = meta[s];
@@ -218,12 +220,18 @@ __global__ void __launch_bounds__(THREADS) sweep_kernel(const SweepParams prm) {
       // pre-multiply the staged values by the gathered operand, striped (IPT independent
       // L2 gathers in flight per thread); the walk below then is the plain column sum.
       double* xw = stage_x(s) + mt.x_off;
+      double g[IPT];
 #pragma unroll
       for (int r = 0; r < IPT; ++r) {
         const int k = tid + r * THREADS;
-        if (k < mt.nk) xw[k] = __dmul_rn(xw[k], __ldg(prm.v + is[k]));
+        g[r] = (k < mt.nk) ? __ldg(prm.v + is[k]) : 0.0;
       }
-      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) {
+        const int k = tid + r * THREADS;
+        if (k < mt.nk) xw[k] = __dmul_rn(xw[k], g[r]);
+      }
+      consumer_sync();
     }
 
     // ---- per-thread merge-path walk ------------------------------------------------------------
@@ -231,6 +239,7 @@ __global__ void __launch_bounds__(THREADS) sweep_kernel(const SweepParams prm) {
     if (d_lo > items) d_lo = items;
     int d_hi = d_lo + IPT;
     if (d_hi > items) d_hi = items;
+    const int n_my = d_hi - d_lo;
     int lo = d_lo > mt.nk ? d_lo - mt.nk : 0;
     int hi = d_lo < mt.nc ? d_lo : mt.nc;
     while (lo < hi) {
@@ -250,7 +259,7 @@ __global__ void __launch_bounds__(THREADS) sweep_kernel(const SweepParams prm) {
       double vc = (mt.c0 + ci < prm.ncol) ? __ldg(prm.v + mt.c0 + ci) : 0.0;
 #pragma unroll
       for (int it = 0; it < IPT; ++it) {
-        if (d_lo + it < d_hi) {
+        if (it < n_my) {
           if (ki < col_end) {
             ptx::red_add_f64(prm.out + is[ki], __dmul_rn(xs[ki], vc));
             ++ki;
@@ -261,89 +270,105 @@ __global__ void __launch_bounds__(THREADS) sweep_kernel(const SweepParams prm) {
           }
         }
       }
-    } else {
+    } else if (n_my == IPT && ki + IPT <= col_end) {
+      // common case (columns much longer than IPT): all my items are entries of one column
+      double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-      for (int it = 0; it < IPT; ++it) {
-        if (d_lo + it < d_hi) {
-          if (ki < col_end) {
-            acc = __dadd_rn(acc, xs[ki]);
-            ++ki;
+      for (int it = 0; it + 1 < IPT; it += 2) {
+        a0 = __dadd_rn(a0, xs[ki + it]);
+        a1 = __dadd_rn(a1, xs[ki + it + 1]);
+      }
+      if (IPT & 1) a0 = __dadd_rn(a0, xs[ki + IPT - 1]);
+      acc = __dadd_rn(a0, a1);
+    } else {
+#pragma unroll 1
+      for (int it = 0; it < n_my; ++it) {
+        if (ki < col_end) {
+          acc = __dadd_rn(acc, xs[ki]);
+          ++ki;
+        } else {
+          if (first_ci < 0) {
+            first_ci = ci;
+            head = acc;
           } else {
-            if (first_ci < 0) {
-              first_ci = ci;
-              head = acc;
-            } else {
-              prm.out[mt.c0 + ci] = finalize(acc, prm.divisor);  // began and ended inside this thread
-            }
-            acc = 0.0;
-            ++ci;
-            col_end = as[ci] - mt.k0;
+            prm.out[mt.c0 + ci] = acc;  // began and ended inside this thread
           }
+          acc = 0.0;
+          ++ci;
+          col_end = as[ci] - mt.k0;
         }
       }
     }
+
+    // this warp no longer reads stage s: hand it back to the producer
+    if (MODE == SWEEP_SPMV_T) ptx::fence_proxy_async_smem();  // my generic writes precede the async refill
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty_bar[s]);
 
     if (REDUCES) {
-      // ---- stitch partial sums across threads: segmented inclusive scan, segment heads are
-      //      threads in which at least one column ended (their tail starts a new column) ----
+      // ---- stitch partial sums across threads.  Segment heads are threads in which at least one
+      //      column ended (their tail starts a new column).  A warp without any column end only
+      //      needs its total; otherwise a segmented inclusive scan over the lanes. ----
+      const int fl_mine = first_ci >= 0 ? 1 : 0;
+      const unsigned ends_in_warp = __ballot_sync(0xffffffffu, fl_mine);
       double sc = acc;
-      int fl = first_ci >= 0 ? 1 : 0;
+      int fl = fl_mine;
+      double prev_sc = 0.0;
+      int prev_fl = 0;
+      if (ends_in_warp == 0u) {
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const double up = __shfl_up_sync(0xffffffffu, sc, off);
-        const int fu = __shfl_up_sync(0xffffffffu, fl, off);
-        if (lane >= off) {
-          if (!fl) sc = __dadd_rn(up, sc);
-          fl |= fu;
+        for (int off = 16; off > 0; off >>= 1) sc = __dadd_rn(sc, __shfl_xor_sync(0xffffffffu, sc, off));
+        if (lane == 31) {
+          warp_sum[buf][warp] = sc;
+          warp_flag[buf][warp] = 0;
         }
-      }
-      if (lane == 31) {
-        warp_sum[warp] = sc;
-        warp_flag[warp] = fl;
-      }
-      double prev_sc = __shfl_up_sync(0xffffffffu, sc, 1);
-      int prev_fl = __shfl_up_sync(0xffffffffu, fl, 1);
-      __syncthreads();
-      // fold the warps before mine (and, continuing, all of them for the next tile's carry)
-      double pre = cta_carry;
-      int pre_fl = 0;
-      double all = cta_carry;
-      int all_fl = 0;
-#pragma unroll
-      for (int w = 0; w < WARPS; ++w) {
-        const double ws = warp_sum[w];
-        const int wf = warp_flag[w];
-        all = wf ? ws : __dadd_rn(all, ws);
-        all_fl |= wf;
-        if (w + 1 == warp) {
-          pre = all;
-          pre_fl = all_fl;
-        }
-      }
-      if (warp == 0) {
-        pre = cta_carry;
-        pre_fl = 0;
-      }
-      double carry_in;
-      int excl_fl;
-      if (lane == 0) {
-        carry_in = pre;
-        excl_fl = pre_fl;
       } else {
-        carry_in = prev_fl ? prev_sc : __dadd_rn(pre, prev_sc);
-        excl_fl = prev_fl | pre_fl;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const double up = __shfl_up_sync(0xffffffffu, sc, off);
+          const int fu = __shfl_up_sync(0xffffffffu, fl, off);
+          if (lane >= off) {
+            if (!fl) sc = __dadd_rn(up, sc);
+            fl |= fu;
+          }
+        }
+        if (lane == 31) {
+          warp_sum[buf][warp] = sc;
+          warp_flag[buf][warp] = fl;
+        }
+        prev_sc = __shfl_up_sync(0xffffffffu, sc, 1);
+        prev_fl = __shfl_up_sync(0xffffffffu, fl, 1);
       }
+      consumer_sync();
+      // fold the warp totals with one lane per warp (every warp does it redundantly: no extra barrier)
+      double ws = (lane < WARPS) ? warp_sum[buf][lane] : 0.0;
+      int wf = (lane < WARPS) ? warp_flag[buf][lane] : 0;
+      if (lane == 0 && !wf) ws = __dadd_rn(cta_carry, ws);
+#pragma unroll
+      for (int off = 1; off < WARPS; off <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, ws, off);
+        const int fu = __shfl_up_sync(0xffffffffu, wf, off);
+        if (lane >= off) {
+          if (!wf) ws = __dadd_rn(up, ws);
+          wf |= fu;
+        }
+      }
+      const int src = warp > 0 ? warp - 1 : 0;
+      double pre = __shfl_sync(0xffffffffu, ws, src);
+      if (warp == 0) pre = cta_carry;
+      const double all = __shfl_sync(0xffffffffu, ws, WARPS - 1);
       if (first_ci >= 0) {
-        const double val = __dadd_rn(carry_in, head);
-        const bool first_of_cta = !cta_seen_end && !excl_fl;
-        prm.out[mt.c0 + first_ci] = (first_of_cta && cta_split_start) ? val : finalize(val, prm.divisor);
+        double carry_in;
+        if (lane == 0)
+          carry_in = pre;
+        else
+          carry_in = prev_fl ? prev_sc : __dadd_rn(pre, prev_sc);
+        // partial sums carried in by EARLIER CTAs (a column spanning CTA boundaries) are added
+        // afterwards, in CTA order, by the last CTA to finish
+        prm.out[mt.c0 + first_ci] = __dadd_rn(carry_in, head);
       }
       cta_carry = all;
-      cta_seen_end = cta_seen_end || (all_fl != 0);
     }
-
-    __syncthreads();  // everyone is done with stage s (and with warp_sum/warp_flag)
-    if (tid == 0 && t_issue < t_end) issue(s);
   }
 
   if (REDUCES) {
@@ -353,11 +378,15 @@ __global__ void __launch_bounds__(THREADS) sweep_kernel(const SweepParams prm) {
       if (n_local > 0 && last_c1 < prm.ncol && last_k1 > __ldg(prm.p + last_c1)) col = last_c1;
       prm.carry_col[blockIdx.x] = col;
       prm.carry_val[blockIdx.x] = cta_carry;
+    }
+    __threadfence();  // every consumer's stores to out[] are visible before the ticket is taken
+    consumer_sync();
+    if (tid == 0) {
       __threadfence();
       const unsigned int t = atomicAdd(prm.ticket, 1u);
       cta_info[1] = (t == gridDim.x - 1) ? 1 : 0;
     }
-    __syncthreads();
+    consumer_sync();
     if (cta_info[1]) {
       __threadfence();
       const int G_ = gridDim.x;
@@ -367,8 +396,8 @@ __global__ void __launch_bounds__(THREADS) sweep_kernel(const SweepParams prm) {
         if (g > 0 && __ldcg(prm.carry_col + g - 1) == col) continue;  // not the first CTA carrying into col
         double tot = 0.0;
         for (int h = g; h < G_ && __ldcg(prm.carry_col + h) == col; ++h) tot = __dadd_rn(tot, __ldcg(prm.carry_val + h));
-        // the CTA in which `col` ends stored its own share un-finalised (cta_split_start)
-        prm.out[col] = finalize(__dadd_rn(tot, __ldcg(prm.out + col)), prm.divisor);
+        // the CTA in which `col` ends stored only its own share (its cta_carry started from 0)
+        prm.out[col] = __dadd_rn(tot, __ldcg(prm.out + col));
       }
       if (tid == 0) *prm.ticket = 0u;  // ready for the next launch
     }
@@ -460,15 +489,15 @@ static SweepConfig sweep_config(SweepMode mode) {
 
 template <int MODE, int STAGES>
 static int launch_sweep_t(sb200_matrix* m, const SweepParams& prm, int ctas_per_sm) {
-  using G = SweepGeom<SWEEP_THREADS>;
+  using G = SweepGeom;
   constexpr bool WITH_I = (MODE == SWEEP_SPMV_T || MODE == SWEEP_SPMV);
   const size_t smem = STAGES * G::stage_bytes(WITH_I);
-  auto kern = sweep_kernel<MODE, SWEEP_THREADS, STAGES>;
+  auto kern = sweep_kernel<MODE, STAGES>;
   SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int64_t grid = static_cast<int64_t>(m->sm_count) * ctas_per_sm;
   if (grid > prm.n_tiles) grid = prm.n_tiles;
   if (grid < 1) return SB200_OK;
-  kern<<<static_cast<unsigned>(grid), SWEEP_THREADS, smem, m->stream>>>(prm);
+  kern<<<static_cast<unsigned>(grid), SWEEP_BLOCK, smem, m->stream>>>(prm);
   count_launch();
   SB_CUDA(cudaGetLastError());
   return SB200_OK;
@@ -476,7 +505,7 @@ static int launch_sweep_t(sb200_matrix* m, const SweepParams& prm, int ctas_per_
 
 template <int MODE>
 static int launch_sweep_m(sb200_matrix* m, const SweepParams& prm, const SweepConfig& cfg) {
-  using G = SweepGeom<SWEEP_THREADS>;
+  using G = SweepGeom;
   constexpr bool WITH_I = (MODE == SWEEP_SPMV_T || MODE == SWEEP_SPMV);
   int stages = cfg.stages, ctas = cfg.ctas_per_sm;
   while (ctas > 1 && static_cast<size_t>(stages) * G::stage_bytes(WITH_I) * ctas > 220 * 1024) --ctas;
@@ -491,7 +520,7 @@ static int launch_sweep_m(sb200_matrix* m, const SweepParams& prm, const SweepCo
 int build_sweep_plan(sb200_matrix* m) {
   const int64_t total = static_cast<int64_t>(m->ncol) + m->nnz;
   m->n_tiles = (total + SWEEP_TILE - 1) / SWEEP_TILE;
-  SB_CUDA(cudaMalloc(&m->d_plan, sizeof(int32_t) * static_cast<size_t>(m->n_tiles + 2)));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&m->d_plan), sizeof(int32_t) * static_cast<size_t>(m->n_tiles + 2), m->stream));
   const int threads = 256;
   const int64_t blocks = (m->n_tiles + 1 + threads - 1) / threads;
   sweep_plan_kernel<<<static_cast<unsigned>(blocks), threads, 0, m->stream>>>(m->d_p, m->ncol, m->nnz, m->n_tiles,
@@ -511,7 +540,19 @@ int launch_vec_div(cudaStream_t s, double* d, int64_t n, double divisor) {
   return SB200_OK;
 }
 
+static bool use_row_bands(const sb200_matrix* m) {
+  // the banded path needs entries and rows; SB200_ROW_PLAN=0 forces the plan-free L2-atomic kernels
+  if (m->nnz == 0 || m->nrow == 0 || m->ncol == 0) return false;
+  const char* e = getenv("SB200_ROW_PLAN");
+  return !(e && e[0] == '0');
+}
+
 int launch_sweep(sb200_matrix* m, SweepMode mode, const double* d_v, double divisor, double* d_out) {
+  if ((mode == SWEEP_ROWSUM || mode == SWEEP_SPMV) && use_row_bands(m)) {
+    SB_TRY(launch_band_scatter(m, mode == SWEEP_SPMV ? d_v : nullptr, d_out));
+    if (mode == SWEEP_ROWSUM && divisor != 0.0) SB_TRY(launch_vec_div(m->stream, d_out, m->nrow, divisor));
+    return SB200_OK;
+  }
   if (mode == SWEEP_ROWSUM || mode == SWEEP_SPMV) {
     // scatter targets start from zero (the reference's zero-initialised NumericVector, RcppSparse.h:139)
     if (m->nrow > 0) SB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * static_cast<size_t>(m->nrow), m->stream));
@@ -542,19 +583,24 @@ int launch_sweep(sb200_matrix* m, SweepMode mode, const double* d_v, double divi
   prm.nnz = static_cast<int32_t>(m->nnz);
   prm.v = d_v;
   prm.out = d_out;
-  prm.divisor = (mode == SWEEP_SPMV) ? 0.0 : divisor;
   // workspace layout: [ticket u32 | pad to 16] [carry_col int32 x 1024] [carry_val f64 x 1024]
   unsigned char* ws = static_cast<unsigned char*>(m->d_ws);
   prm.ticket = reinterpret_cast<unsigned int*>(ws);
   prm.carry_col = reinterpret_cast<int32_t*>(ws + 16);
   prm.carry_val = reinterpret_cast<double*>(ws + 16 + 4 * 1024);
   const SweepConfig cfg = sweep_config(mode);
+  int rc;
   switch (mode) {
-    case SWEEP_COLSUM: return launch_sweep_m<SWEEP_COLSUM>(m, prm, cfg);
-    case SWEEP_SPMV_T: return launch_sweep_m<SWEEP_SPMV_T>(m, prm, cfg);
-    case SWEEP_SPMV: return launch_sweep_m<SWEEP_SPMV>(m, prm, cfg);
+    case SWEEP_COLSUM: rc = launch_sweep_m<SWEEP_COLSUM>(m, prm, cfg); break;
+    case SWEEP_SPMV_T: rc = launch_sweep_m<SWEEP_SPMV_T>(m, prm, cfg); break;
+    case SWEEP_SPMV: rc = launch_sweep_m<SWEEP_SPMV>(m, prm, cfg); break;
     default: return fail(SB200_E_INVALID, "unknown sweep mode");
   }
+  SB_TRY(rc);
+  // colMeans: sums[c] / Dim[0] as a second pass over the ncol outputs, exactly the reference's
+  // structure (RcppSparse.h:146-148); 16 B per column next to 8 B per stored entry.
+  if (mode == SWEEP_COLSUM && divisor != 0.0) SB_TRY(launch_vec_div(m->stream, d_out, m->ncol, divisor));
+  return SB200_OK;
 }
 
 }  // namespace sb200
