@@ -47,8 +47,8 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", help="C1|C2|C3|C4 (default C2 = BASELINE configs[1])")
     ap.add_argument("--scale", type=float, default=1.0, help="column-count scale of the workload (tests)")
@@ -86,11 +86,13 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Started well before the timed region (nvidia-smi needs ~1 s to produce its first line)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -98,7 +100,18 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def wait_first_sample(self, timeout=5.0):
+        t_end = time.perf_counter() + timeout
+        while self.proc and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.02)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc:
@@ -107,8 +120,13 @@ class ClockSampler:
                 self.proc.wait(timeout=5)
             except Exception:
                 pass
+        inside = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.05]
+        where = "during the timed region"
+        if not inside:  # region shorter than one sampling period: take the samples right around it
+            inside = [r for (t, r) in self.rows if self.t0 is not None and abs(t - self.t0) < 0.5]
+            where = "within 0.5 s of the timed region (region shorter than the sampling period)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -121,7 +139,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sampled": where}
 
 
 # =====================================================================================================
@@ -167,9 +185,11 @@ def run_reference(args, ops):
     from rcppsparse_b200 import synth
 
     spec = synth.config(args.workload, args.scale)
-    block = cpu_block(spec, args.cpu_cols)
+    # bounded sample: keep the whole --steps/--warmup run within about a minute of CPU work
+    cols = max(1000, min(args.cpu_cols, int(args.cpu_cols * 100 / max(1, args.steps + args.warmup))))
+    block = cpu_block(spec, cols)
     nnz = int(block[2].shape[0])
-    for _ in range(max(1, args.warmup // 3)):
+    for _ in range(max(1, min(args.warmup, 3))):
         time_cpu(ops, block, 1)
     kind = "port"
     step_s = []
@@ -249,17 +269,19 @@ def run_b200(args, ops):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         for op in ops:
             run_op(op)
     barrier()
-
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.wait_first_sample()
     launches0 = _lib.lib().sb200_launch_count()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(ops) + 1)] for _ in range(args.steps)]
     barrier()
+    sampler.mark_begin()
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
         ev[s][0].record()
@@ -268,6 +290,7 @@ def run_b200(args, ops):
             ev[s][k + 1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    sampler.mark_end()
     launches = _lib.lib().sb200_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 

@@ -1,0 +1,261 @@
+// RcppSparse.h — drop-in replacement header: the same RcppSparse::Matrix class, with the
+// data-parallel sweeps served by libsparse_b200 (NVIDIA B200, sm_100a) through the C ABI in
+// sparse_b200.h.  No CPU fallback: if the library reports an error the method throws.
+//
+// Same public surface as the reference header (zdebruine/RcppSparse, inst/include/RcppSparse.h):
+//   members x, i, p, Dim                                   reference :29-30   (zero-copy Rcpp handles)
+//   constructors (4 vectors / S4 / default)                reference :33-42
+//   rows cols nrow ncol n_nonzero nonzeros innerIndexPtr outerIndexPtr InnerNNZs   :44-51, :357-359
+//   colSums rowSums colMeans rowMeans                      reference :131-156  -> sb200_col_sums ... sb200_row_means
+//   transpose (and the vignette's t)                       reference :375-385  -> sb200_transpose
+//   wrap, clone, at, operator(), operator[]                reference :387-394, :54-73 (host side, unchanged semantics)
+//   InnerIterator                                          reference :218-233 (host side, unchanged)
+//   Rcpp::traits::Exporter<RcppSparse::Matrix>             reference :398-423
+// Additions: spmv(v) = A v and spmv_t(v) = A^T v (the reference only has the iterator idiom),
+// refresh() after mutating x in place, release() to drop the device mirror early.
+// Not provided here (off the hot path): crossprod, the range/row iterators,
+// dense block extraction, isAppxSymmetric, InnerIndices.
+//
+// Include order: like the reference, this header must come BEFORE <Rcpp.h> in a translation unit
+// (it forward-declares the Exporter specialisation between <RcppCommon.h> and <Rcpp.h>).
+#ifndef RCPPSPARSE_B200_DROPIN_H
+#define RCPPSPARSE_B200_DROPIN_H
+
+#include <RcppCommon.h>
+
+namespace RcppSparse {
+class Matrix;
+}
+
+namespace Rcpp {
+namespace traits {
+template <>
+class Exporter<RcppSparse::Matrix>;
+}
+}  // namespace Rcpp
+
+#include <Rcpp.h>
+
+#include <cstdlib>
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+#include "sparse_b200.h"
+
+namespace RcppSparse {
+
+namespace b200 {
+
+// status -> C++ exception; BEGIN_RCPP/END_RCPP turn it into an R error (reference src/RcppExports.cpp:17,23)
+inline void check(int status) {
+  if (status == SB200_OK) return;
+  const std::string what = std::string("libsparse_b200: ") + sb200_last_error();
+  if (status == SB200_E_INVALID || status == SB200_E_STRUCTURE) throw std::invalid_argument(what);
+  throw std::runtime_error(what);
+}
+
+inline int device_from_env() {
+  const char* e = std::getenv("SB200_DEVICE");
+  return e ? std::atoi(e) : 0;
+}
+
+// Owner of one device mirror.  Held through a shared_ptr by the Matrix: copies of a Matrix alias the
+// same R vectors (Rcpp handle semantics), so they share the mirror too; it is destroyed with the last
+// copy.  There is no cache keyed by host address across objects — R may reuse addresses after a GC
+// (SURVEY.md H4); the addresses below only detect that THIS object's members were re-pointed.
+struct Mirror {
+  sb200_matrix* handle = nullptr;
+  // the slots the handle was uploaded from: if the public members are re-pointed afterwards
+  // (m.x = other; the vignette allows it, Documentation.Rmd:235-236) the mirror is rebuilt
+  const void *src_x = nullptr, *src_i = nullptr, *src_p = nullptr;
+  long src_nnz = -1;
+  int src_nrow = -1, src_ncol = -1;
+  Mirror() = default;
+  Mirror(const Mirror&) = delete;
+  Mirror& operator=(const Mirror&) = delete;
+  void drop() {
+    if (handle) sb200_matrix_destroy(handle);
+    handle = nullptr;
+  }
+  ~Mirror() { drop(); }
+};
+
+}  // namespace b200
+
+class Matrix {
+public:
+  // the dgCMatrix slots, aliased not copied
+  Rcpp::NumericVector x;
+  Rcpp::IntegerVector i, p, Dim;
+
+  Matrix(Rcpp::NumericVector x_, Rcpp::IntegerVector i_, Rcpp::IntegerVector p_, Rcpp::IntegerVector Dim_)
+      : x(x_), i(i_), p(p_), Dim(Dim_), mirror_(std::make_shared<b200::Mirror>()) {}
+
+  Matrix(const Rcpp::S4& s) : mirror_(std::make_shared<b200::Mirror>()) {
+    const char* needed[] = {"x", "p", "i", "Dim"};
+    for (const char* name : needed)
+      if (!s.hasSlot(name)) throw std::invalid_argument("Cannot construct RcppSparse::Matrix from this S4 object");
+    x = s.slot("x");
+    i = s.slot("i");
+    p = s.slot("p");
+    Dim = s.slot("Dim");
+  }
+
+  Matrix() : mirror_(std::make_shared<b200::Mirror>()) {}
+
+  // ---- dimensions and handles ------------------------------------------------------------------
+  unsigned int rows() { return Dim[0]; }
+  unsigned int cols() { return Dim[1]; }
+  unsigned int nrow() { return Dim[0]; }
+  unsigned int ncol() { return Dim[1]; }
+  unsigned int n_nonzero() { return x.size(); }
+  Rcpp::NumericVector& nonzeros() { return x; }
+  Rcpp::IntegerVector& innerIndexPtr() { return i; }
+  Rcpp::IntegerVector& outerIndexPtr() { return p; }
+  unsigned int InnerNNZs(int col) { return p[col + 1] - p[col]; }
+
+  // deep copy of the four vectors; the copy gets its own (lazy) mirror
+  Matrix clone() { return Matrix(Rcpp::clone(x), Rcpp::clone(i), Rcpp::clone(p), Rcpp::clone(Dim)); }
+
+  // ---- point lookups stay on the host (latency-bound; rows are sorted inside a column) -------------
+  double at(int row, int col) const {
+    for (int k = p[col], end = p[col + 1]; k < end && i[k] <= row; ++k)
+      if (i[k] == row) return x[k];
+    return 0.0;
+  }
+  double operator()(int row, int col) const { return at(row, col); }
+  double operator[](int index) const { return x[index]; }
+
+  // ---- the sweeps: one kernel launch each behind the C ABI --------------------------------------------
+  Rcpp::NumericVector colSums() {
+    Rcpp::NumericVector sums(Dim[1]);
+    b200::check(sb200_col_sums(mirror(), sums.begin()));
+    return sums;
+  }
+  Rcpp::NumericVector rowSums() {
+    Rcpp::NumericVector sums(Dim[0]);
+    b200::check(sb200_row_sums(mirror(), sums.begin()));
+    return sums;
+  }
+  Rcpp::NumericVector colMeans() {
+    Rcpp::NumericVector means(Dim[1]);
+    b200::check(sb200_col_means(mirror(), means.begin()));
+    return means;
+  }
+  Rcpp::NumericVector rowMeans() {
+    Rcpp::NumericVector means(Dim[0]);
+    b200::check(sb200_row_means(mirror(), means.begin()));
+    return means;
+  }
+
+  // y = A v (v has ncol entries) and y = A^T v (v has nrow entries)
+  Rcpp::NumericVector spmv(const Rcpp::NumericVector& v) {
+    if (v.size() != Dim[1]) throw std::invalid_argument("spmv: v must have ncol entries");
+    Rcpp::NumericVector y(Dim[0]);
+    b200::check(sb200_spmv(mirror(), v.begin(), y.begin()));
+    return y;
+  }
+  Rcpp::NumericVector spmv_t(const Rcpp::NumericVector& v) {
+    if (v.size() != Dim[0]) throw std::invalid_argument("spmv_t: v must have nrow entries");
+    Rcpp::NumericVector y(Dim[1]);
+    b200::check(sb200_spmv_t(mirror(), v.begin(), y.begin()));
+    return y;
+  }
+
+  // canonical CSC of A^T; the result owns fresh R vectors (no call back into the R interpreter)
+  Matrix transpose() {
+    const long nnz = x.size();
+    Rcpp::IntegerVector tp(long(Dim[0]) + 1), ti(nnz), tdim(2);
+    Rcpp::NumericVector tx(nnz);
+    tdim[0] = Dim[1];
+    tdim[1] = Dim[0];
+    b200::check(sb200_transpose(mirror(), tp.begin(), ti.begin(), tx.begin()));
+    return Matrix(tx, ti, tp, tdim);
+  }
+  Matrix t() { return transpose(); }
+
+  Rcpp::S4 wrap() {
+    Rcpp::S4 s(std::string("dgCMatrix"));
+    s.slot("x") = x;
+    s.slot("i") = i;
+    s.slot("p") = p;
+    s.slot("Dim") = Dim;
+    return s;
+  }
+
+  // The view aliases R memory; after changing x in place call refresh() so the mirror follows.
+  void refresh() {
+    if (mirror_->handle) b200::check(sb200_matrix_refresh_values(mirror_->handle, x.begin()));
+  }
+  void release() { mirror_->drop(); }
+
+  // ---- column cursor, host side: same protocol as the reference ---------------------------------------
+  class InnerIterator {
+  public:
+    InnerIterator(Matrix& m, int col) : m_(m), col_(col), at_(m.p[col]), end_(m.p[col + 1]) {}
+    operator bool() const { return at_ < end_; }
+    InnerIterator& operator++() {
+      ++at_;
+      return *this;
+    }
+    const double& value() const { return m_.x[at_]; }
+    int row() const { return m_.i[at_]; }
+    int col() const { return col_; }
+
+  private:
+    Matrix& m_;
+    int col_, at_, end_;
+  };
+
+private:
+  // Created with the object (empty), so that copies made at any time share one holder: a copy of a
+  // Matrix aliases the same R vectors and must see the same device state.
+  std::shared_ptr<b200::Mirror> mirror_;
+
+  // one-time upload of i/p/x (pinned in place for the copy), tied to this object and its copies
+  sb200_matrix* mirror() {
+    b200::Mirror& m = *mirror_;
+    const bool same = m.handle && m.src_x == static_cast<const void*>(x.begin()) &&
+                      m.src_i == static_cast<const void*>(i.begin()) && m.src_p == static_cast<const void*>(p.begin()) &&
+                      m.src_nnz == long(x.size()) && m.src_nrow == Dim[0] && m.src_ncol == Dim[1];
+    if (!same) {
+      m.drop();
+      if (Dim.size() != 2 || p.size() != long(Dim[1]) + 1 || i.size() != x.size())
+        throw std::invalid_argument("RcppSparse::Matrix: slot lengths inconsistent with Dim");
+      b200::check(sb200_matrix_create(i.begin(), p.begin(), x.begin(), Dim[0], Dim[1], x.size(),
+                                      b200::device_from_env(), SB200_PIN_HOST, &m.handle));
+      m.src_x = x.begin();
+      m.src_i = i.begin();
+      m.src_p = p.begin();
+      m.src_nnz = long(x.size());
+      m.src_nrow = Dim[0];
+      m.src_ncol = Dim[1];
+    }
+    return m.handle;
+  }
+};
+
+}  // namespace RcppSparse
+
+namespace Rcpp {
+namespace traits {
+
+// Rcpp::as<RcppSparse::Matrix>: capture the four slot handles of a dgCMatrix, no copy
+template <>
+class Exporter<RcppSparse::Matrix> {
+public:
+  Exporter(SEXP obj) : s_(obj) {
+    if (!s_.hasSlot("x") || !s_.hasSlot("p") || !s_.hasSlot("i") || !s_.hasSlot("Dim"))
+      throw std::invalid_argument("Cannot construct RcppSparse::Matrix from this S4 object");
+  }
+  RcppSparse::Matrix get() { return RcppSparse::Matrix(s_); }
+
+private:
+  Rcpp::S4 s_;
+};
+
+}  // namespace traits
+}  // namespace Rcpp
+
+#endif  // RCPPSPARSE_B200_DROPIN_H

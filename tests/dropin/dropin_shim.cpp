@@ -1,0 +1,112 @@
+// Test harness for the drop-in C++ header: user-level code exactly as a downstream Rcpp package
+// would write it against RcppSparse::Matrix, compiled against the Rcpp stand-in (R and Rcpp are not
+// installed here) and linked to libsparse_b200.  The extern "C" wrappers only move raw arrays in
+// and out so that pytest can drive it with ctypes.
+#include <RcppSparse.h>  // the drop-in header from include/
+
+#include <cstdint>
+#include <cstring>
+#include <string>
+
+// The package's exported function (reference src/example.cpp:26-32) in the drop-in build: the sweep is
+// one call on the class instead of a serial InnerIterator loop.
+Rcpp::NumericVector columnSums(RcppSparse::Matrix& A) { return A.colSums(); }
+
+// A downstream user's own iterator loop keeps working unchanged (host side, reference idiom).
+static Rcpp::NumericVector column_sums_by_iterator(RcppSparse::Matrix& A) {
+  Rcpp::NumericVector sums(A.cols());
+  for (size_t col = 0; col < A.cols(); ++col)
+    for (RcppSparse::Matrix::InnerIterator it(A, col); it; ++it) sums(col) += it.value();
+  return sums;
+}
+
+namespace {
+thread_local std::string g_err;
+
+RcppSparse::Matrix view(const int* i, const int* p, const double* x, int nrow, int ncol, int64_t nnz) {
+  return RcppSparse::Matrix(Rcpp::NumericVector::view(const_cast<double*>(x), long(nnz)),
+                            Rcpp::IntegerVector::view(const_cast<int*>(i), long(nnz)),
+                            Rcpp::IntegerVector::view(const_cast<int*>(p), long(ncol) + 1),
+                            Rcpp::IntegerVector({nrow, ncol}));
+}
+void out(const Rcpp::NumericVector& v, double* dst) {
+  if (v.size() > 0) std::memcpy(dst, v.begin(), sizeof(double) * size_t(v.size()));
+}
+template <typename F>
+int guarded(F f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::invalid_argument& e) {
+    g_err = std::string("invalid_argument: ") + e.what();
+    return 1;
+  } catch (const std::exception& e) {
+    g_err = std::string("runtime_error: ") + e.what();
+    return 2;
+  }
+}
+}  // namespace
+
+extern "C" {
+const char* dropin_last_error() { return g_err.c_str(); }
+
+// op: 0 columnSums (exported fn), 1 colSums, 2 rowSums, 3 colMeans, 4 rowMeans, 5 iterator loop on the host
+int dropin_reduce(int op, const int* i, const int* p, const double* x, int nrow, int ncol, int64_t nnz, double* dst) {
+  return guarded([&] {
+    RcppSparse::Matrix A = view(i, p, x, nrow, ncol, nnz);
+    switch (op) {
+      case 0: out(columnSums(A), dst); break;
+      case 1: out(A.colSums(), dst); break;
+      case 2: out(A.rowSums(), dst); break;
+      case 3: out(A.colMeans(), dst); break;
+      case 4: out(A.rowMeans(), dst); break;
+      default: out(column_sums_by_iterator(A), dst); break;
+    }
+  });
+}
+int dropin_spmv(int transposed, const int* i, const int* p, const double* x, int nrow, int ncol, int64_t nnz,
+                const double* v, double* y) {
+  return guarded([&] {
+    RcppSparse::Matrix A = view(i, p, x, nrow, ncol, nnz);
+    Rcpp::NumericVector vv = Rcpp::NumericVector::view(const_cast<double*>(v), transposed ? nrow : ncol);
+    out(transposed ? A.spmv_t(vv) : A.spmv(vv), y);
+  });
+}
+int dropin_transpose(const int* i, const int* p, const double* x, int nrow, int ncol, int64_t nnz, int* tp, int* ti,
+                     double* tx, int* tdim) {
+  return guarded([&] {
+    RcppSparse::Matrix A = view(i, p, x, nrow, ncol, nnz);
+    RcppSparse::Matrix T = A.t();
+    std::memcpy(tp, T.p.begin(), sizeof(int) * size_t(T.p.size()));
+    if (nnz > 0) {
+      std::memcpy(ti, T.i.begin(), sizeof(int) * size_t(nnz));
+      std::memcpy(tx, T.x.begin(), sizeof(double) * size_t(nnz));
+    }
+    tdim[0] = T.Dim[0];
+    tdim[1] = T.Dim[1];
+    // round trip through wrap() and the Exporter, as Rcpp::as<RcppSparse::Matrix> would do
+    Rcpp::S4 s = T.wrap();
+    RcppSparse::Matrix back = Rcpp::traits::Exporter<RcppSparse::Matrix>(s.get()).get();
+    if (back.x.size() != T.x.size() || back.rows() != T.rows()) throw std::runtime_error("wrap/as round trip");
+  });
+}
+// copies share one mirror; clone() does not; in-place edits need refresh()
+int dropin_alias_semantics(const int* i, const int* p, double* x, int nrow, int ncol, int64_t nnz, double* before,
+                           double* after) {
+  return guarded([&] {
+    RcppSparse::Matrix A = view(i, p, x, nrow, ncol, nnz);
+    RcppSparse::Matrix B = A;  // aliases the same vectors and the same device mirror
+    out(B.colSums(), before);
+    x[0] += 1000.0;
+    A.refresh();
+    out(B.colSums(), after);
+  });
+}
+int dropin_missing_slot() {
+  return guarded([&] {
+    Rcpp::S4 s(std::string("dgCMatrix"));
+    s.slot("x") = Rcpp::NumericVector(1);
+    RcppSparse::Matrix bad(s);
+  });
+}
+}

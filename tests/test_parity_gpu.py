@@ -131,6 +131,24 @@ def test_synth_transpose_bit_exact(synth_case, checker):
     A.release()
 
 
+@pytest.mark.parametrize("row_plan", ["0", "1"])
+@pytest.mark.parametrize("case", ["C2_scaled", "C3_scaled", "many_tiny_columns"])
+def test_row_indexed_ops_on_both_paths(row_plan, case, monkeypatch, checker):
+    """rowSums / rowMeans / A v have a plan-free L2-atomic kernel and a banded shared-memory kernel;
+    the library picks by shape.  Both must meet the parity bar on every shape."""
+    monkeypatch.setenv("SB200_ROW_PLAN", row_plan)
+    spec = SYNTH_CASES[case]()
+    i, p, x = synth.generate_host(spec)
+    nrow, ncol = spec.nrow, spec.ncol
+    args = (i, p, x, nrow, ncol)
+    A = Matrix(x, i, p, np.array([nrow, ncol], np.int32))
+    oracle.assert_within("rowSums", A.rowSums(), checker.rowSums(*args), *args, tol=TOL)
+    oracle.assert_within("rowMeans", A.rowMeans(), checker.rowMeans(*args), *args, tol=TOL)
+    v = synth.dense_vector(spec.seed, ncol)
+    oracle.assert_within("spmv", A.spmv(v), checker.spmv(*args, v), *args, v=v, tol=TOL)
+    A.release()
+
+
 @pytest.mark.parametrize("bands", [1, 2, 7, 64, 300])
 def test_transpose_is_independent_of_band_count(bands, monkeypatch, checker):
     """The band decomposition is an implementation detail: any band count gives the same bits."""
