@@ -81,7 +81,8 @@ class GpuLocal:
 
 class ShardedMatrix:
     """The reference's Matrix methods (RcppSparse.h:131-156 + the SpMV idiom) over a column-sharded matrix.
-    Every method returns the FULL result vector on every rank."""
+    Every method returns the FULL result vector on every rank — as a view of an internal buffer that
+    the next call of the same kind (column- or row-indexed) overwrites: clone it to keep it."""
 
     def __init__(self, local: LocalSweeps, bounds: Sequence[int], rank: int, group=None, device=None):
         self.local = local
