@@ -15,9 +15,9 @@ At N > 1 (torchrun, one rank per GPU) every rank owns a C2-sized column block of
 1M x (100k*N) matrix (weak scaling; columns are independent units), column results are
 all-gathered and row results all-reduced over NCCL inside the timed step.
 
-Extra keys beside the base contract: `per_op`, `roofline` (dominant kernel: the rowSums stream
-kernel, algorithmic bytes 12*nnz + 8*nrow per launch, timed live with CUDA events on the
-launching stream), `cpu_baseline` (reference code on a bounded column block, rank 0, N=1),
+Extra keys beside the base contract: `per_op`, `roofline` (dominant kernel: the rowSums kernel —
+banded shared-memory scatter at C2 — algorithmic bytes 12*nnz + 8*nrow per launch, timed live with
+CUDA events on the launching stream), `cpu_baseline` (reference code on a bounded column block, rank 0, N=1),
 `e2e` (same step through the host-buffer C ABI: upload of i/p/x from pinned memory + four
 results read back, every step), `clocks`, `gpu_launches`.
 """
@@ -324,7 +324,8 @@ def run_b200(args, ops):
                       "algorithmic_bytes": ab, "achieved_GBps": gbs, "frac_of_measured": gbs / peak,
                       "frac_of_nominal_8TBps": gbs / NOMINAL_HBM_GBS}
     dom = max(ops, key=lambda o: per_op_ms[o])
-    dom_kernel = {"rowSums": "rowsum_stream_kernel", "rowMeans": "rowsum_stream_kernel", "colSums": "sweep_kernel<COLSUM>",
+    row_kernel = "band_scatter_kernel" if D.row_path() == "banded" else "rowsum_stream_kernel"
+    dom_kernel = {"rowSums": row_kernel, "rowMeans": row_kernel, "colSums": "sweep_kernel<COLSUM>",
                   "colMeans": "sweep_kernel<COLSUM>", "spmv": "sweep_kernel<SPMV>", "spmv_t": "sweep_kernel<SPMV_T>",
                   "transpose": "transpose_band_kernel"}[dom]
     roofline = {"bound": "hbm", "kernel": dom_kernel, "op": dom, "achieved": per_op[dom]["achieved_GBps"], "peak": peak,
@@ -338,6 +339,7 @@ def run_b200(args, ops):
         "metric": METRIC, "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(spec, args, ops, nnz), "per_op": per_op, "roofline": roofline,
+        "row_path": D.row_path(),
         "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
     }
 

@@ -111,6 +111,11 @@ int sb200_transpose_dev(sb200_matrix* m, sb200_matrix** out);
 /* d[k] /= divisor for k < n, on the handle's stream (mean scaling after a cross-rank reduce). */
 int sb200_vec_div_dev(sb200_matrix* m, double* d, int64_t n, double divisor);
 
+/* Which kernel serves the row-indexed sweeps of this matrix: *banded = 1 shared-memory row bands
+ * (a band plan is built on first use and cached with the mirror), 0 = plan-free L2 atomics.
+ * Decided once per handle from the shape; SB200_ROW_PLAN=0/1 overrides. */
+int sb200_matrix_row_path(sb200_matrix* m, int* banded);
+
 /* ---- introspection for benchmarks ----------------------------------------------------------
  * Number of kernel launches this library has issued in this process (all handles). */
 int64_t sb200_launch_count(void);

@@ -343,19 +343,41 @@ struct ScatterArgs {
   BandView bv;
   const double* v;  // [ncol] or null (rowSums)
   double* out;      // [nrow]; pre-zeroed when S > 1
+  int max_rows;     // accumulator capacity (rows of the widest band)
+  // Lockstep: the CTAs of one column split advance through the columns together (a soft barrier every
+  // `lock_every` chunks), so the 32-byte sectors that neighbouring bands share are fetched from HBM
+  // once and hit L2 for everyone else.  Needs all CTAs co-resident (cooperative launch); 0 = off.
+  int lock_every;
+  unsigned int* lock_counters;  // [S], zeroed before the launch
 };
 
+constexpr int SC_CAPW = 512;  // flattened entries a warp stages per round
+
+static size_t scatter_smem_bytes(int max_rows, bool spmv) {
+  return sizeof(double) * static_cast<size_t>(max_rows > 0 ? max_rows : 1) + BAND_WARPS * SC_CAPW * sizeof(int32_t) +
+         (spmv ? BAND_WARPS * SC_CAPW : 0) + 16;
+}
+
+// CTA (band b, column split h).  A warp takes 32 consecutive columns of the chunk, one run descriptor
+// per lane.  Instead of searching the run of every entry, each lane EXPANDS its own run into the
+// warp's flat list in shared memory (entry index per slot; ~1 store per entry), then the lanes walk
+// the list 32 slots at a time, so consecutive lanes read consecutive entries of a run (coalesced),
+// U loads in flight before the first shared-memory FP64 add.
 template <bool SPMV>
 __global__ void __launch_bounds__(BAND_THREADS) band_scatter_kernel(const ScatterArgs a) {
-  extern __shared__ double acc[];
+  extern __shared__ __align__(16) unsigned char ssm[];
   const BandView& bv = a.bv;
+  const int MR = a.max_rows;
+  double* acc = reinterpret_cast<double*>(ssm);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int32_t* flat = reinterpret_cast<int32_t*>(acc + MR) + warp * SC_CAPW;
+  uint8_t* flatl = reinterpret_cast<uint8_t*>(reinterpret_cast<int32_t*>(acc + MR) + BAND_WARPS * SC_CAPW) + warp * SC_CAPW;
+  constexpr int U = BAND_UNROLL;
   const int units = bv.nb * bv.S;
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
     const int h = u / bv.nb, b = u % bv.nb;  // consecutive CTAs = consecutive bands of one split
     const int32_t row0 = bv.rb[b];
-    const int32_t R = bv.rb[b + 1] - row0;
-    if (R <= 0) continue;
+    const int32_t R = bv.rb[b + 1] - row0;  // an empty band still takes part in the split's barriers
     const int32_t c_lo = bv.cs[h], c_hi = bv.cs[h + 1];
     __syncthreads();
     for (int r = tid; r < R; r += BAND_THREADS) acc[r] = 0.0;
@@ -366,44 +388,94 @@ __global__ void __launch_bounds__(BAND_THREADS) band_scatter_kernel(const Scatte
     double nv = 0.0;
     {
       const int64_t c = static_cast<int64_t>(c_lo) + tid;
-      if (c < c_hi) {
+      if (c < c_hi && R > 0) {
         ns = band_start(bv, b, c);
         ne = band_start(bv, b + 1, c);
         if (SPMV) nv = __ldg(a.v + c);
       }
     }
-    for (int64_t cbase = c_lo; cbase < c_hi; cbase += BAND_CH) {
-      const int32_t s = ns, e = ne;
+    int chunk_no = 0;
+    for (int64_t cbase = c_lo; cbase < c_hi; cbase += BAND_CH, ++chunk_no) {
+      if (a.lock_every > 0 && chunk_no % a.lock_every == 0) {
+        // soft barrier across the bv.nb CTAs of split h (all resident: cooperative launch)
+        __syncthreads();
+        if (tid == 0) {
+          const unsigned int target = static_cast<unsigned int>(bv.nb) * (chunk_no / a.lock_every + 1);
+          atomicAdd(a.lock_counters + h, 1u);
+          unsigned int seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.lock_counters + h) : "memory");
+            if (seen < target) __nanosleep(64);
+          } while (seen < target);
+        }
+        __syncthreads();
+      }
+      const int32_t s = ns, len = ne - ns;
       const double vc = nv;
       ns = ne = 0;
       nv = 0.0;
       {
         const int64_t c = cbase + BAND_CH + tid;
-        if (c < c_hi) {
+        if (c < c_hi && R > 0) {
           ns = band_start(bv, b, c);
           ne = band_start(bv, b + 1, c);
           if (SPMV) nv = __ldg(a.v + c);
-          for (int32_t k = ns & ~31; k < ne; k += 32) ptx::prefetch_l2(bv.i + k);
-          for (int32_t k = ns & ~15; k < ne; k += 16) ptx::prefetch_l2(bv.x + k);
+          if (a.lock_every == 0) {  // without lockstep, at least pull the next runs towards L2 early
+            for (int32_t k = ns & ~31; k < ne; k += 32) ptx::prefetch_l2(bv.i + k);
+            for (int32_t k = ns & ~15; k < ne; k += 16) ptx::prefetch_l2(bv.x + k);
+          }
         }
       }
-      warp_walk_runs<BAND_UNROLL, ScatterItem>(
-          s, e - s, lane,
-          [&](int32_t k, int l, bool valid) {
-            ScatterItem it;
-            it.r = -1;
-            it.xv = 0.0;
-            it.w = 1.0;
-            if (SPMV) it.w = __shfl_sync(0xffffffffu, vc, l);
-            if (valid) {
-              it.r = ptx::ld_stream_s32(bv.i + k) - row0;
-              it.xv = ptx::ld_stream_f64(bv.x + k);
+      int32_t incl = len;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int32_t up = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += up;
+      }
+      const int32_t excl = incl - len;
+      const int32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      for (int32_t base = 0; base < total; base += SC_CAPW) {  // one round unless the runs are long
+        // owner expansion of the slots [base, base + SC_CAPW)
+        int32_t j0 = base - excl;
+        if (j0 < 0) j0 = 0;
+        int32_t j1 = base + SC_CAPW - excl;
+        if (j1 > len) j1 = len;
+        for (int32_t j = j0; j < j1; ++j) {
+          flat[excl + j - base] = s + j;
+          if (SPMV) flatl[excl + j - base] = static_cast<uint8_t>(lane);
+        }
+        __syncwarp();
+        int32_t n = total - base;
+        if (n > SC_CAPW) n = SC_CAPW;
+        for (int32_t q0 = 0; q0 < n; q0 += 32 * U) {
+          int32_t rr[U];
+          double xx[U];
+#pragma unroll
+          for (int t = 0; t < U; ++t) {
+            const int32_t q = q0 + t * 32 + lane;
+            rr[t] = -1;
+            xx[t] = 0.0;
+            if (q < n) {
+              const int32_t k = flat[q];
+              rr[t] = ptx::ld_stream_s32(bv.i + k) - row0;
+              xx[t] = ptx::ld_stream_f64(bv.x + k);
             }
-            return it;
-          },
-          [&](const ScatterItem& it) {
-            if (it.r >= 0) atomicAdd(&acc[it.r], SPMV ? __dmul_rn(it.xv, it.w) : it.xv);
-          });
+          }
+          if (SPMV) {
+#pragma unroll
+            for (int t = 0; t < U; ++t) {
+              const int32_t q = q0 + t * 32 + lane;
+              const int l = (q < n) ? flatl[q] : 0;
+              const double w = __shfl_sync(0xffffffffu, vc, l);
+              xx[t] = __dmul_rn(xx[t], w);
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < U; ++t)
+            if (rr[t] >= 0) atomicAdd(&acc[rr[t]], xx[t]);
+        }
+        __syncwarp();
+      }
     }
     __syncthreads();
     if (bv.S == 1) {
@@ -746,6 +818,61 @@ static BandView make_view(const sb200_matrix* m, const BandPlan* bp) {
 // ---- row-indexed sums ----------------------------------------------------------------------------------
 constexpr int SCATTER_ROWS_CAP = 12288;  // 96 KB of FP64 accumulators: two CTAs per SM
 
+namespace {
+// columns (non-empty) whose length is below `thresh`: their band runs would be shorter than ~3 entries
+__global__ void short_columns_kernel(const int32_t* __restrict__ gp, int32_t ncol, int32_t thresh,
+                                     unsigned int* __restrict__ out /* [2]: short, non-empty */) {
+  unsigned int n_short = 0, n_some = 0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < ncol; c += stride) {
+    const int32_t len = gp[c + 1] - gp[c];
+    if (len > 0) {
+      ++n_some;
+      if (len < thresh) ++n_short;
+    }
+  }
+  n_short = __reduce_add_sync(0xffffffffu, n_short);
+  n_some = __reduce_add_sync(0xffffffffu, n_some);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, n_short);
+    atomicAdd(out + 1, n_some);
+  }
+}
+}  // namespace
+
+// Which kernel serves rowSums / rowMeans / A v for this matrix (decided once per handle):
+//   banded (1) when popular rows would serialise the L2 atomics (small row range), or when columns
+//   are long enough that a band's run per column is several entries; the plan-free L2-atomic path (0)
+//   when many columns are short (skewed column lengths: runs of 1-2 entries waste sectors).
+// Measured on B200: C2 (uniform, 1000/col) banded 0.50 vs 0.60 ms; C3 (30k rows) 22 vs 42 ms;
+// C4 (power-law columns) 12.9 vs 11.6 ms.
+int decide_row_path(sb200_matrix* m) {
+  if (m->row_path >= 0) return SB200_OK;
+  int path = 0;
+  if (m->nnz > 0 && m->nrow > 0 && m->ncol > 0) {
+    if (m->nrow <= 65536) {
+      path = 1;
+    } else {
+      unsigned int* d_cnt = reinterpret_cast<unsigned int*>(static_cast<unsigned char*>(m->d_ws) + 16 + 4 * 1024 + 8 * 1024);
+      SB_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned int), m->stream));
+      int64_t blocks = (static_cast<int64_t>(m->ncol) + 255) / 256;
+      if (blocks > m->sm_count * 8) blocks = m->sm_count * 8;
+      short_columns_kernel<<<static_cast<unsigned>(blocks), 256, 0, m->stream>>>(m->d_p, m->ncol, 3 * m->sm_count, d_cnt);
+      count_launch();
+      SB_CUDA(cudaGetLastError());
+      unsigned int h[2] = {0, 0};
+      SB_CUDA(cudaMemcpyAsync(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
+      SB_CUDA(cudaStreamSynchronize(m->stream));
+      SB_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned int), m->stream));
+      path = (h[1] > 0 && 4ull * h[0] <= h[1]) ? 1 : 0;  // at most a quarter of the columns are short
+    }
+  }
+  if (const char* e = getenv("SB200_ROW_PLAN")) path = (e[0] != '0') ? 1 : 0;
+  if (m->nnz == 0 || m->nrow == 0 || m->ncol == 0) path = 0;
+  m->row_path = path;
+  return SB200_OK;
+}
+
 int ensure_scatter_plan(sb200_matrix* m) {
   if (m->plan_scatter) return SB200_OK;
   const int bands = m->sm_count;      // one band per SM ...
@@ -765,19 +892,44 @@ int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out) {
   a.v = d_v;
   a.out = d_out;
   if (bp->S > 1) SB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * static_cast<size_t>(m->nrow), m->stream));
-  const size_t smem = sizeof(double) * static_cast<size_t>(bp->max_rows > 0 ? bp->max_rows : 1);
+  a.max_rows = (bp->max_rows > 0 ? bp->max_rows : 1);
+  const size_t smem = scatter_smem_bytes(a.max_rows, d_v != nullptr);
   int ctas = static_cast<int>((200 * 1024) / (smem + 2048));
   if (ctas > 2) ctas = 2;
   if (ctas < 1) ctas = 1;
   int grid = m->sm_count * ctas;
   if (grid > bp->nb * bp->S) grid = bp->nb * bp->S;
-  if (d_v) {
-    SB_CUDA(cudaFuncSetAttribute(band_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    band_scatter_kernel<true><<<grid, BAND_THREADS, smem, m->stream>>>(a);
-  } else {
-    SB_CUDA(cudaFuncSetAttribute(band_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    band_scatter_kernel<false><<<grid, BAND_THREADS, smem, m->stream>>>(a);
+  // lockstep every few chunks: the columns in flight (all resident splits) should stay well inside L2
+  // measured (profiles/r01): barriers every 1/2/4/8 chunks cost more than the L2 hits they buy at C2
+  // (0.73/0.63/0.57/0.54 ms vs 0.50 ms free-running with L2 prefetch), so lockstep is off by default
+  int lock_every = 0;
+  if (const char* e = getenv("SB200_LOCKSTEP")) lock_every = atoi(e);
+  if (lock_every < 0) lock_every = 0;
+  if (bp->S > 1024) lock_every = 0;
+  a.lock_every = lock_every;
+  a.lock_counters = reinterpret_cast<unsigned int*>(static_cast<unsigned char*>(m->d_ws) + 16 + 4 * 1024 + 8 * 1024);
+  if (lock_every > 0 && static_cast<size_t>(bp->S) * 4 > m->ws_bytes - (16 + 4 * 1024 + 8 * 1024)) a.lock_every = 0;
+  auto kern = d_v ? reinterpret_cast<const void*>(&band_scatter_kernel<true>)
+                  : reinterpret_cast<const void*>(&band_scatter_kernel<false>);
+  SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  if (a.lock_every > 0) {
+    // a soft barrier between CTAs is only safe if they are all resident: ask the driver to guarantee it
+    SB_CUDA(cudaMemsetAsync(a.lock_counters, 0, sizeof(unsigned int) * bp->S, m->stream));
+    void* params[] = {&a};
+    cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(BAND_THREADS), params, smem, m->stream);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources) {
+      cudaGetLastError();
+      a.lock_every = 0;  // fall back to free-running CTAs
+    } else {
+      SB_CUDA(e);
+      count_launch();
+      return SB200_OK;
+    }
   }
+  if (d_v)
+    band_scatter_kernel<true><<<grid, BAND_THREADS, smem, m->stream>>>(a);
+  else
+    band_scatter_kernel<false><<<grid, BAND_THREADS, smem, m->stream>>>(a);
   count_launch();
   SB_CUDA(cudaGetLastError());
   return SB200_OK;

@@ -101,6 +101,7 @@ static int new_handle(int device, int32_t nrow, int32_t ncol, int64_t nnz, sb200
   if (!m) return fail(SB200_E_NOMEM, "host allocation failed");
   memset(m, 0, sizeof(*m));
   m->magic = MATRIX_MAGIC;
+  m->row_path = -1;
   m->device = device;
   m->nrow = nrow;
   m->ncol = ncol;
@@ -140,7 +141,7 @@ int alloc_matrix(int device, int32_t nrow, int32_t ncol, int64_t nnz, sb200_matr
 }
 
 int finish_matrix(sb200_matrix* m, unsigned flags) {
-  m->ws_bytes = 16 + 4 * 1024 + 8 * 1024 + 64;
+  m->ws_bytes = 16 + 4 * 1024 + 8 * 1024 + 4 * 1024;  // sweep ticket + carries, then lockstep counters
   SB_TRY(pool_alloc(&m->d_ws, m->ws_bytes, m->stream));
   SB_CUDA(cudaMemsetAsync(m->d_ws, 0, m->ws_bytes, m->stream));
   m->stage_len = (m->nrow > m->ncol ? m->nrow : m->ncol);
@@ -409,6 +410,14 @@ int sb200_transpose(sb200_matrix* m, int32_t* p_out, int32_t* i_out, double* x_o
   free_matrix(t);
   if (rc != SB200_OK) return rc;
   if (e != cudaSuccess) return cuda_fail(e, "download of the transposed matrix", __FILE__, __LINE__);
+  return SB200_OK;
+}
+
+int sb200_matrix_row_path(sb200_matrix* m, int* banded) {
+  ENTER(m);
+  if (!banded) return fail(SB200_E_INVALID, "banded is NULL");
+  SB_TRY(decide_row_path(m));
+  *banded = m->row_path;
   return SB200_OK;
 }
 

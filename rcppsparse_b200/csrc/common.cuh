@@ -76,6 +76,7 @@ struct sb200_matrix {
   int64_t stage_len;
   // row-band plan for the row-indexed sweeps (bands.cu); structure-only, built on first use
   sb200::BandPlan* plan_scatter;
+  int row_path;  // -1 undecided, 0 plan-free L2 atomics, 1 banded (decide_row_path)
 };
 
 namespace sb200 {
@@ -118,6 +119,7 @@ int exclusive_scan_u32(cudaStream_t s, const uint32_t* d_in, int32_t* d_out, int
 // bands.cu
 int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double* d_x_out);
 int ensure_scatter_plan(sb200_matrix* m);
+int decide_row_path(sb200_matrix* m);
 int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out);  // d_v null = rowSums
 void free_matrix_plans(sb200_matrix* m, cudaStream_t s);
 

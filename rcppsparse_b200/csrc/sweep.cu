@@ -540,21 +540,9 @@ int launch_vec_div(cudaStream_t s, double* d, int64_t n, double divisor) {
   return SB200_OK;
 }
 
-static bool use_row_bands(const sb200_matrix* m) {
-  // Two ways to produce a row-indexed result (measured in profiles/r01):
-  //  * plan-free: one RED.F64 per entry at L2 — ~160 G/s on B200 whatever the row, but entries of a
-  //    popular row serialise at one L2 slice (30k x 1M scRNA-like config: 42 ms);
-  //  * banded (bands.cu): rows owned by one CTA in shared memory — immune to popular rows (24 ms
-  //    there), currently slower than the L2 path when rows are many and evenly hit.
-  // Default: banded when the row range is small enough for popular rows to matter; SB200_ROW_PLAN=0/1
-  // forces one or the other.
-  if (m->nnz == 0 || m->nrow == 0 || m->ncol == 0) return false;
-  if (const char* e = getenv("SB200_ROW_PLAN")) return e[0] != '0';
-  return m->nrow <= 65536;
-}
-
 int launch_sweep(sb200_matrix* m, SweepMode mode, const double* d_v, double divisor, double* d_out) {
-  if ((mode == SWEEP_ROWSUM || mode == SWEEP_SPMV) && use_row_bands(m)) {
+  if (mode == SWEEP_ROWSUM || mode == SWEEP_SPMV) SB_TRY(decide_row_path(m));
+  if ((mode == SWEEP_ROWSUM || mode == SWEEP_SPMV) && m->row_path == 1) {
     SB_TRY(launch_band_scatter(m, mode == SWEEP_SPMV ? d_v : nullptr, d_out));
     if (mode == SWEEP_ROWSUM && divisor != 0.0) SB_TRY(launch_vec_div(m->stream, d_out, m->nrow, divisor));
     return SB200_OK;

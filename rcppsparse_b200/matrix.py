@@ -124,6 +124,12 @@ class DeviceMatrix:
         check(_lib.lib().sb200_algorithmic_bytes(self._h, op.encode(), C.byref(n)))
         return n.value
 
+    def row_path(self) -> str:
+        """'banded' or 'l2-atomics': which kernel serves rowSums / rowMeans / A v for this matrix."""
+        b = C.c_int()
+        check(_lib.lib().sb200_matrix_row_path(self._h, C.byref(b)))
+        return "banded" if b.value else "l2-atomics"
+
     def refresh_values(self, x) -> None:
         check(_lib.lib().sb200_matrix_refresh_values(self._h, _ptr(x)))
 

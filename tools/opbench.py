@@ -80,7 +80,7 @@ def main():
             ms.append(e0.elapsed_time(e1))
         ab = D.algorithmic_bytes(ABI[op])
         best, med = float(np.min(ms)), float(np.median(ms))
-        print(json.dumps({"tag": a.tag, "cfg": os.environ.get("SB200_SWEEP_CFG", ""), "workload": spec.name, "op": op,
+        print(json.dumps({"tag": a.tag, "cfg": os.environ.get("SB200_SWEEP_CFG", ""), "workload": spec.name, "op": op, "row_path": D.row_path(),
                           "nnz": D.nnz, "ms_best": round(best, 4), "ms_median": round(med, 4),
                           "Gnnz_per_s": round(D.nnz / med / 1e6, 2), "GBps": round(ab / med / 1e6, 1),
                           "frac_measured": round(ab / med / 1e6 / peak, 3)}), flush=True)
