@@ -349,6 +349,7 @@ struct ScatterArgs {
   // once and hit L2 for everyone else.  Needs all CTAs co-resident (cooperative launch); 0 = off.
   int lock_every;
   unsigned int* lock_counters;  // [S], zeroed before the launch
+  int cluster;                  // CTAs per thread-block cluster (adjacent bands), 1 = no clusters
 };
 
 constexpr int SC_CAPW = 512;  // flattened entries a warp stages per round
@@ -396,6 +397,12 @@ __global__ void __launch_bounds__(BAND_THREADS) band_scatter_kernel(const Scatte
     }
     int chunk_no = 0;
     for (int64_t cbase = c_lo; cbase < c_hi; cbase += BAND_CH, ++chunk_no) {
+      if (a.cluster > 1) {
+        // the CTAs of a cluster own ADJACENT bands of the same split: keep them on the same chunk
+        // (hardware cluster barrier), so the sectors their neighbouring runs share are fetched once
+        asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+      }
       if (a.lock_every > 0 && chunk_no % a.lock_every == 0) {
         // soft barrier across the bv.nb CTAs of split h (all resident: cooperative launch)
         __syncthreads();
@@ -915,6 +922,7 @@ int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out) {
   if (a.lock_every > 0) {
     // a soft barrier between CTAs is only safe if they are all resident: ask the driver to guarantee it
     SB_CUDA(cudaMemsetAsync(a.lock_counters, 0, sizeof(unsigned int) * bp->S, m->stream));
+    a.cluster = 1;
     void* params[] = {&a};
     cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(BAND_THREADS), params, smem, m->stream);
     if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources) {
@@ -925,6 +933,37 @@ int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out) {
       count_launch();
       return SB200_OK;
     }
+  }
+  // clusters of adjacent bands: every CTA of a cluster must walk the same number of chunks, i.e. be in
+  // the same split in every round => cluster size divides the band count and the grid
+  // measured (profiles/r01): a cluster barrier per chunk does cut HBM traffic but costs far more than it
+  // saves (C2 rowSums 0.52 ms free-running, 0.71 ms with clusters of 2, 1.17 ms with clusters of 4) => off
+  int cluster = 1;
+  if (const char* e = getenv("SB200_SCATTER_CLUSTER")) cluster = atoi(e);
+  while (cluster > 1 && (bp->nb % cluster != 0 || grid % cluster != 0)) cluster >>= 1;
+  if (cluster < 1) cluster = 1;
+  a.cluster = cluster;
+  if (cluster > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(BAND_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = m->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = d_v ? cudaLaunchKernelEx(&cfg, band_scatter_kernel<true>, a)
+                        : cudaLaunchKernelEx(&cfg, band_scatter_kernel<false>, a);
+    if (e == cudaSuccess) {
+      count_launch();
+      return SB200_OK;
+    }
+    cudaGetLastError();  // cluster launch not possible with this footprint: free-running CTAs
+    a.cluster = 1;
   }
   if (d_v)
     band_scatter_kernel<true><<<grid, BAND_THREADS, smem, m->stream>>>(a);

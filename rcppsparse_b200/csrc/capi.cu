@@ -82,6 +82,7 @@ static void free_matrix(sb200_matrix* m) {
   }
   free_matrix_plans(m, fs);
   pool_free(m->d_plan, fs);
+  pool_free(m->d_plan_g, fs);
   pool_free(m->d_ws, fs);
   pool_free(m->d_stage_in, fs);
   pool_free(m->d_stage_out, fs);

@@ -38,8 +38,13 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 // column end; a tile is SWEEP_TILE consecutive items on the merge path of (p[1..ncol], 0..nnz).
 // ---------------------------------------------------------------------------------------------
 constexpr int SWEEP_THREADS = 256;
-constexpr int SWEEP_IPT = 15;  // odd => conflict-free 8-byte shared-memory reads at stride IPT
-constexpr int SWEEP_TILE = SWEEP_THREADS * SWEEP_IPT;  // 3840 items
+// items per thread, odd => conflict-free 8-byte shared-memory reads at stride IPT.  Two geometries
+// (measured, profiles/r01): the plain column sums want 11 (34 KB stages, 3 CTAs/SM: 83-101 % of peak),
+// the gather/scatter sweeps want 7 (29 KB stages, 3 CTAs/SM: more warps to hide the L2 gathers).
+constexpr int SWEEP_IPT = 11;
+constexpr int SWEEP_TILE = SWEEP_THREADS * SWEEP_IPT;  // 2816 items per tile (also the band-pointer tiling)
+constexpr int GATHER_IPT = 7;
+constexpr int GATHER_TILE = SWEEP_THREADS * GATHER_IPT;  // 1792 items per tile
 
 constexpr int NUM_SMS_B200 = 148;
 
@@ -67,6 +72,8 @@ struct sb200_matrix {
   // merge-path plan: plan[t] = number of column ends before diagonal t*SWEEP_TILE (t = 0..n_tiles)
   int32_t* d_plan;
   int64_t n_tiles;
+  int32_t* d_plan_g;  // same, every GATHER_TILE items
+  int64_t n_tiles_g;
   // per-launch workspace (carries, tickets), zeroed where the kernels expect zero
   void* d_ws;
   size_t ws_bytes;

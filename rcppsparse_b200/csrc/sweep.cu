@@ -88,8 +88,9 @@ struct StageMeta {
   int32_t pad;
 };
 
+template <int IPT_>
 struct SweepGeom {
-  static constexpr int TILE = SWEEP_TILE;
+  static constexpr int TILE = SWEEP_THREADS * IPT_;
   static constexpr int X_ELEMS = TILE + 2;   // +1 align-down slack, +1 round-up
   static constexpr int A_ELEMS = TILE + 8;   // nc+1 values, +3 align-down, +3 round-up, +1 spare
   static constexpr int I_ELEMS = TILE + 8;
@@ -106,10 +107,10 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 
 template <int MODE, int STAGES>
 __global__ void __launch_bounds__(SWEEP_BLOCK) sweep_kernel(const SweepParams prm) {
-  using G = SweepGeom;
+  constexpr int IPT = (MODE == SWEEP_COLSUM) ? SWEEP_IPT : GATHER_IPT;
+  using G = SweepGeom<IPT>;
   constexpr int THREADS = SWEEP_THREADS;
   constexpr int TILE = G::TILE;
-  constexpr int IPT = SWEEP_IPT;
   constexpr bool WITH_I = (MODE == SWEEP_SPMV_T || MODE == SWEEP_SPMV);
   constexpr bool REDUCES = (MODE == SWEEP_COLSUM || MODE == SWEEP_SPMV_T);
   constexpr int WARPS = THREADS / 32;
@@ -470,16 +471,12 @@ static SweepConfig sweep_config(SweepMode mode) {
   // overrides (tuning runs only).
   SweepConfig c;
   c.threads = SWEEP_THREADS;
-  if (mode == SWEEP_COLSUM) {
-    c.stages = 2;
-    c.ctas_per_sm = 2;
-  } else {
-    c.stages = 3;
-    c.ctas_per_sm = 1;
-  }
+  c.stages = 2;       // measured best for every mode: two stages per CTA ...
+  c.ctas_per_sm = 3;  // ... and three CTAs per SM (24 consumer warps) rather than deeper rings
+  (void)mode;
   if (const char* e = getenv("SB200_SWEEP_CFG")) {
     int t = 0, s = 0, k = 0;
-    if (sscanf(e, "%d,%d,%d", &t, &s, &k) == 3 && t == SWEEP_THREADS && s >= 2 && s <= 4 && k >= 1 && k <= 4) {
+    if (sscanf(e, "%d,%d,%d", &t, &s, &k) == 3 && t == SWEEP_THREADS && s >= 2 && s <= 4 && k >= 1 && k <= 8) {
       c.stages = s;
       c.ctas_per_sm = k;
     }
@@ -487,15 +484,19 @@ static SweepConfig sweep_config(SweepMode mode) {
   return c;
 }
 
+template <int MODE>
+using GeomOf = SweepGeom<(MODE == SWEEP_COLSUM) ? SWEEP_IPT : GATHER_IPT>;
+
 template <int MODE, int STAGES>
 static int launch_sweep_t(sb200_matrix* m, const SweepParams& prm, int ctas_per_sm) {
-  using G = SweepGeom;
+  using G = GeomOf<MODE>;
   constexpr bool WITH_I = (MODE == SWEEP_SPMV_T || MODE == SWEEP_SPMV);
   const size_t smem = STAGES * G::stage_bytes(WITH_I);
   auto kern = sweep_kernel<MODE, STAGES>;
   SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int64_t grid = static_cast<int64_t>(m->sm_count) * ctas_per_sm;
   if (grid > prm.n_tiles) grid = prm.n_tiles;
+  if (grid > 1024) grid = 1024;  // capacity of the cross-CTA carry arrays in the workspace
   if (grid < 1) return SB200_OK;
   kern<<<static_cast<unsigned>(grid), SWEEP_BLOCK, smem, m->stream>>>(prm);
   count_launch();
@@ -505,7 +506,7 @@ static int launch_sweep_t(sb200_matrix* m, const SweepParams& prm, int ctas_per_
 
 template <int MODE>
 static int launch_sweep_m(sb200_matrix* m, const SweepParams& prm, const SweepConfig& cfg) {
-  using G = SweepGeom;
+  using G = GeomOf<MODE>;
   constexpr bool WITH_I = (MODE == SWEEP_SPMV_T || MODE == SWEEP_SPMV);
   int stages = cfg.stages, ctas = cfg.ctas_per_sm;
   while (ctas > 1 && static_cast<size_t>(stages) * G::stage_bytes(WITH_I) * ctas > 220 * 1024) --ctas;
@@ -517,16 +518,22 @@ static int launch_sweep_m(sb200_matrix* m, const SweepParams& prm, const SweepCo
   }
 }
 
-int build_sweep_plan(sb200_matrix* m) {
+static int build_one_plan(sb200_matrix* m, int tile, int32_t** d_plan, int64_t* n_tiles) {
   const int64_t total = static_cast<int64_t>(m->ncol) + m->nnz;
-  m->n_tiles = (total + SWEEP_TILE - 1) / SWEEP_TILE;
-  SB_TRY(pool_alloc(reinterpret_cast<void**>(&m->d_plan), sizeof(int32_t) * static_cast<size_t>(m->n_tiles + 2), m->stream));
+  *n_tiles = (total + tile - 1) / tile;
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(d_plan), sizeof(int32_t) * static_cast<size_t>(*n_tiles + 2), m->stream));
   const int threads = 256;
-  const int64_t blocks = (m->n_tiles + 1 + threads - 1) / threads;
-  sweep_plan_kernel<<<static_cast<unsigned>(blocks), threads, 0, m->stream>>>(m->d_p, m->ncol, m->nnz, m->n_tiles,
-                                                                            SWEEP_TILE, m->d_plan);
+  const int64_t blocks = (*n_tiles + 1 + threads - 1) / threads;
+  sweep_plan_kernel<<<static_cast<unsigned>(blocks), threads, 0, m->stream>>>(m->d_p, m->ncol, m->nnz, *n_tiles, tile,
+                                                                            *d_plan);
   count_launch();
   SB_CUDA(cudaGetLastError());
+  return SB200_OK;
+}
+
+int build_sweep_plan(sb200_matrix* m) {
+  SB_TRY(build_one_plan(m, SWEEP_TILE, &m->d_plan, &m->n_tiles));
+  SB_TRY(build_one_plan(m, GATHER_TILE, &m->d_plan_g, &m->n_tiles_g));
   return SB200_OK;
 }
 
@@ -571,8 +578,8 @@ int launch_sweep(sb200_matrix* m, SweepMode mode, const double* d_v, double divi
   prm.i = m->d_i;
   prm.p = m->d_p;
   prm.x = m->d_x;
-  prm.plan = m->d_plan;
-  prm.n_tiles = m->n_tiles;
+  prm.plan = (mode == SWEEP_COLSUM) ? m->d_plan : m->d_plan_g;
+  prm.n_tiles = (mode == SWEEP_COLSUM) ? m->n_tiles : m->n_tiles_g;
   prm.ncol = m->ncol;
   prm.nnz = static_cast<int32_t>(m->nnz);
   prm.v = d_v;
