@@ -418,6 +418,9 @@ def measure_e2e(args, ops, D, nnz, device):
 
 
 def main():
+    # NCCL prints a version banner on stdout at init when NCCL_DEBUG=VERSION/INFO is in the environment;
+    # rank 0 must print exactly one JSON line
+    os.environ["NCCL_DEBUG"] = os.environ.get("SB200_NCCL_DEBUG", "WARN")
     args = parse_args()
     ops = tuple(o for o in args.ops.split(",") if o)
     for o in ops:
