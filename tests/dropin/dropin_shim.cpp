@@ -102,6 +102,20 @@ int dropin_alias_semantics(const int* i, const int* p, double* x, int nrow, int 
     out(B.colSums(), after);
   });
 }
+// public members may be re-pointed after construction (vignette: "m2.x = x; m2.i = i; ..."): the mirror follows
+int dropin_repointed_members(const int* i, const int* p, const double* x1, const double* x2, int nrow, int ncol,
+                             int64_t nnz, double* sums1, double* sums2) {
+  return guarded([&] {
+    RcppSparse::Matrix A;  // default-constructed, then filled slot by slot
+    A.i = Rcpp::IntegerVector::view(const_cast<int*>(i), long(nnz));
+    A.p = Rcpp::IntegerVector::view(const_cast<int*>(p), long(ncol) + 1);
+    A.Dim = Rcpp::IntegerVector({nrow, ncol});
+    A.x = Rcpp::NumericVector::view(const_cast<double*>(x1), long(nnz));
+    out(A.colSums(), sums1);
+    A.x = Rcpp::NumericVector::view(const_cast<double*>(x2), long(nnz));  // another vector: new upload
+    out(A.colSums(), sums2);
+  });
+}
 int dropin_missing_slot() {
   return guarded([&] {
     Rcpp::S4 s(std::string("dgCMatrix"));

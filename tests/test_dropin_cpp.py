@@ -26,6 +26,7 @@ def shim():
     L.dropin_spmv.argtypes = [C.c_int, _i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _f64, _f64]
     L.dropin_transpose.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _i32, _i32, _f64, _i32]
     L.dropin_alias_semantics.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _f64, _f64]
+    L.dropin_repointed_members.argtypes = [_i32, _i32, _f64, _f64, C.c_int, C.c_int, C.c_int64, _f64, _f64]
     return L
 
 
@@ -82,6 +83,15 @@ def test_dropin_copies_share_the_mirror_and_refresh(shim):
     before, after = np.empty(2), np.empty(2)
     assert shim.dropin_alias_semantics(i, p, x, 2, 2, 3, before, after) == 0, shim.dropin_last_error()
     assert before.tolist() == [3.0, 3.0] and after.tolist() == [1003.0, 3.0]
+
+
+@pytest.mark.gpu
+def test_dropin_repointed_members_rebuild_the_mirror(shim):
+    i, p = np.array([0, 1, 0], np.int32), np.array([0, 2, 3], np.int32)
+    x1, x2 = np.array([1.0, 2.0, 3.0]), np.array([10.0, 20.0, 30.0])
+    s1, s2 = np.empty(2), np.empty(2)
+    assert shim.dropin_repointed_members(i, p, x1, x2, 2, 2, 3, s1, s2) == 0, shim.dropin_last_error()
+    assert s1.tolist() == [3.0, 3.0] and s2.tolist() == [30.0, 30.0]
 
 
 @pytest.mark.gpu

@@ -262,6 +262,40 @@ def test_corrupt_structure_is_an_error_not_ub(what):
     assert ei.value.code == _lib.E_STRUCTURE
 
 
+def test_pinned_upload_path_and_row_path_report():
+    """SB200_PIN_HOST (cudaHostRegister on caller-owned pages, what the C++ header uses for R memory)
+    gives the same results; the library reports which row-indexed kernel it picked."""
+    spec = synth.config("C2", 0.01)
+    i, p, x = synth.generate_host(spec)
+    args = (i, p, x, spec.nrow, spec.ncol)
+    chk = oracle.best()
+    with DeviceMatrix.from_host(i, p, x, spec.nrow, spec.ncol, pin=True) as D:
+        oracle.assert_within("colSums", D.col_sums(), chk.colSums(*args), *args, tol=TOL)
+        oracle.assert_within("rowSums", D.row_sums(), chk.rowSums(*args), *args, tol=TOL)
+        assert D.row_path() in ("banded", "l2-atomics")
+    small = synth.powerlaw_spec(3000, 500, 50.0, 5)
+    si, sp_, sx = synth.generate_host(small)
+    with DeviceMatrix.from_host(si, sp_, sx, small.nrow, small.ncol) as D:
+        assert D.row_path() == "banded"  # few rows: popular rows would serialise the L2 atomics
+
+
+def test_two_mirrors_and_interleaved_ops_do_not_interfere():
+    a, b = synth.config("C1"), synth.powerlaw_spec(7000, 2000, 80.0, 9, row_levels=5)
+    ia, pa, xa = synth.generate_host(a)
+    ib, pb, xb = synth.generate_host(b)
+    chk = oracle.best()
+    A = Matrix(xa, ia, pa, np.array([a.nrow, a.ncol], np.int32))
+    B = Matrix(xb, ib, pb, np.array([b.nrow, b.ncol], np.int32))
+    for _ in range(3):
+        ra, rb = A.rowSums(), B.rowSums()
+        ca, cb = A.colSums(), B.colSums()
+    oracle.assert_within("rowSums", ra, chk.rowSums(ia, pa, xa, a.nrow, a.ncol), ia, pa, xa, a.nrow, a.ncol, tol=TOL)
+    oracle.assert_within("rowSums", rb, chk.rowSums(ib, pb, xb, b.nrow, b.ncol), ib, pb, xb, b.nrow, b.ncol, tol=TOL)
+    oracle.assert_within("colSums", ca, chk.colSums(ia, pa, xa, a.nrow, a.ncol), ia, pa, xa, a.nrow, a.ncol, tol=TOL)
+    oracle.assert_within("colSums", cb, chk.colSums(ib, pb, xb, b.nrow, b.ncol), ib, pb, xb, b.nrow, b.ncol, tol=TOL)
+    A.release(), B.release()
+
+
 def test_launch_counter_counts_kernels():
     before = _lib.lib().sb200_launch_count()
     A = Matrix(np.array([1.0]), np.array([0], np.int32), np.array([0, 1], np.int32), np.array([1, 1], np.int32))
