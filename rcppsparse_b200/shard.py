@@ -53,6 +53,14 @@ class LocalSweeps(Protocol):
     def spmv(self, v_local: torch.Tensor, out: torch.Tensor) -> None: ...
     def spmv_t(self, v: torch.Tensor, out: torch.Tensor) -> None: ...
     def div(self, t: torch.Tensor, divisor: float) -> None: ...
+    def transpose_local(self): ...  # -> (p int32[nrow+1], cols int32[nnz] local ids, vals float64[nnz]) on the device
+
+
+class _CudaView:
+    """__cuda_array_interface__ shim: a raw device pointer as a tensor, no copy."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 class GpuLocal:
@@ -77,6 +85,23 @@ class GpuLocal:
 
     def div(self, t, divisor):
         self.dm.vec_div_dev(t, t.numel(), divisor)
+
+    def transpose_local(self):
+        """Transpose this rank's column block on the device; the result arrays are viewed as torch tensors
+        without copying (the DeviceMatrix that owns them is kept alive alongside)."""
+        T = self.dm.transpose_dev()
+        T.sync()
+        pi, pp, px = T.device_arrays()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        p = torch.as_tensor(_CudaView(pp, T.ncol + 1, "<i4"), device=dev)
+        if T.nnz > 0:
+            i = torch.as_tensor(_CudaView(pi, T.nnz, "<i4"), device=dev)
+            x = torch.as_tensor(_CudaView(px, T.nnz, "<f8"), device=dev)
+        else:
+            i = torch.empty(0, dtype=torch.int32, device=dev)
+            x = torch.empty(0, dtype=torch.float64, device=dev)
+        self._keep_t = T
+        return p, i, x
 
 
 class ShardedMatrix:
@@ -150,3 +175,64 @@ class ShardedMatrix:
         """A v: v[ncol] replicated; each rank uses only its own slice."""
         self.local.spmv(v[self.c0:self.c1], self._row_full)
         return self._reduce_rows()
+
+    # ---- transpose: local transposes + ONE exchange step (all-to-all-v) --------------------------------------
+    def transpose(self):
+        """CSC of A^T, row-sharded.  Every rank transposes its own column block with the
+        device kernel; row r of the result is the concatenation, in rank (= column) order, of each rank's
+        row-r segment, so order inside a row is ascending source column by construction.  Rows are then
+        dealt out in nnz-balanced contiguous blocks: one all-gather of the per-rank row counts, one
+        all-to-all-v of (column id, value) pairs, and an index gather that interleaves the received
+        per-rank segments row by row.
+
+        Returns (row_bounds, p, cols, vals): this rank owns output columns (= rows of A)
+        [row_bounds[rank], row_bounds[rank+1]); p is rebased to 0; cols are GLOBAL column ids of A."""
+        W, rank, dev = self.world, self.rank, self.device
+        tp, tcols, tvals = self.local.transpose_local()
+        tp64 = tp.to(torch.int64)
+        counts = (tp64[1:] - tp64[:-1]).contiguous()                      # entries of each row in my block
+        if W > 1:
+            flat = torch.empty(W * self.nrow, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(flat, counts, group=self.group)
+            all_counts = flat.view(W, self.nrow)
+        else:
+            all_counts = counts.view(1, -1)
+        total = all_counts.sum(dim=0)                                       # global entries per row
+        P = torch.zeros(self.nrow + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(total, 0, out=P[1:])
+        nnz = int(P[-1])
+        # nnz-balanced contiguous row blocks (same rule as the column split, applied to p')
+        targets = torch.tensor([(nnz * k) // W for k in range(1, W)], dtype=torch.int64, device=dev)
+        inner = torch.searchsorted(P, targets, right=False).clamp_(0, self.nrow).tolist() if W > 1 else []
+        rb = [0] + [max(0, int(v)) for v in inner] + [self.nrow]
+        for k in range(1, len(rb)):
+            rb[k] = max(rb[k], rb[k - 1])
+        r0, r1 = rb[rank], rb[rank + 1]
+        # what I send to rank k: my entries of rows [rb[k], rb[k+1]) — one contiguous slice of my local transpose
+        send_off = [int(tp64[rb[k]]) for k in range(W + 1)]
+        send_splits = [send_off[k + 1] - send_off[k] for k in range(W)]
+        my_counts = all_counts[:, r0:r1]                                    # [W, R]: segment lengths per (source, my row)
+        recv_splits = [int(v) for v in my_counts.sum(dim=1).tolist()]
+        gcols = (tcols.to(torch.int64) + self.c0).to(torch.int32)           # global column ids
+        n_recv = sum(recv_splits)
+        rcols = torch.empty(n_recv, dtype=torch.int32, device=dev)
+        rvals = torch.empty(n_recv, dtype=torch.float64, device=dev)
+        if W > 1:
+            dist.all_to_all_single(rcols, gcols, recv_splits, send_splits, group=self.group)
+            dist.all_to_all_single(rvals, tvals.contiguous(), recv_splits, send_splits, group=self.group)
+        else:
+            rcols.copy_(gcols)
+            rvals.copy_(tvals)
+        # interleave: destination order is (row, source); the received order is (source, row)
+        R = r1 - r0
+        p_own = torch.zeros(R + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(total[r0:r1], 0, out=p_own[1:])
+        if n_recv > 0 and W > 1:
+            seg_len = my_counts.t().reshape(-1)                              # [(row, source)]
+            recv_base = torch.tensor([0] + recv_splits[:-1], dtype=torch.int64, device=dev).cumsum(0)
+            within = torch.cumsum(my_counts, dim=1) - my_counts              # start of row r inside source j's slice
+            seg_src = (recv_base.view(-1, 1) + within).t().reshape(-1)       # where each (row, source) segment sits in recv
+            seg_dst = torch.cumsum(seg_len, 0) - seg_len                     # and where it goes
+            src_index = torch.repeat_interleave(seg_src - seg_dst, seg_len) + torch.arange(n_recv, device=dev)
+            rcols, rvals = rcols[src_index], rvals[src_index]
+        return rb, p_own.to(torch.int32), rcols, rvals

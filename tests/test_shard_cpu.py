@@ -37,6 +37,10 @@ class OracleLocal:
     def div(self, t, divisor):
         t.div_(divisor)
 
+    def transpose_local(self):
+        ti, tp, tx = self.o.transpose(self.i, self.p, self.x, self.nrow, self.ncol)
+        return torch.from_numpy(tp), torch.from_numpy(ti), torch.from_numpy(tx)
+
 
 def _free_port():
     with socket.socket() as s:
@@ -71,6 +75,14 @@ def _worker(rank, world, port, balanced, q):
         }
         for op, (got, want, v) in checks.items():
             oracle.assert_within(op, got, want, *args, v=v)
+        # sharded transpose: my row block of A^T must equal the same rows of the full transpose, bit for bit
+        rb, tp_own, tcols, tvals = S.transpose()
+        fi, fp, fx = full.transpose(*args)
+        r0, r1 = rb[rank], rb[rank + 1]
+        assert rb[0] == 0 and rb[-1] == spec.nrow and all(rb[k] <= rb[k + 1] for k in range(world))
+        assert np.array_equal(tp_own.numpy(), fp[r0:r1 + 1] - fp[r0])
+        assert np.array_equal(tcols.numpy(), fi[fp[r0]:fp[r1]])
+        assert np.array_equal(tvals.numpy().view(np.uint64), fx[fp[r0]:fp[r1]].view(np.uint64))
         q.put((rank, "ok", bounds))
     except Exception as e:  # surface the failure in the parent
         q.put((rank, f"FAIL {type(e).__name__}: {e}", None))

@@ -40,9 +40,16 @@ def main():
                     ("spmv_t", lambda: S.spmv_t(v_r), chk.spmv_t(*args, v_r.cpu().numpy()), v_r.cpu().numpy())):
                 r = oracle.assert_within(op, run().cpu().numpy(), want, *args, v=v)
                 worst[op] = max(worst.get(op, 0.0), r)
+            # sharded transpose (local device transposes + one NCCL all-to-all-v): my rows, bit for bit
+            rb, tp_own, tcols, tvals = S.transpose()
+            fi, fp, fx = chk.transpose(*args)
+            r0, r1 = rb[rank], rb[rank + 1]
+            assert np.array_equal(tp_own.cpu().numpy(), fp[r0:r1 + 1] - fp[r0]), "sharded transpose: p differs"
+            assert np.array_equal(tcols.cpu().numpy(), fi[fp[r0]:fp[r1]]), "sharded transpose: column ids differ"
+            assert np.array_equal(tvals.cpu().numpy().view(np.uint64), fx[fp[r0]:fp[r1]].view(np.uint64))
             D.close()
     dist.barrier()
-    print(f"rank {rank}/{world}: sharded parity ok, worst |err|/sum|a| " + ", ".join(f"{k} {v:.1e}" for k, v in worst.items()))
+    print(f"rank {rank}/{world}: sharded parity ok (sums, SpMV, transpose bit-exact), worst |err|/sum|a| " + ", ".join(f"{k} {v:.1e}" for k, v in worst.items()))
     dist.destroy_process_group()
 
 
