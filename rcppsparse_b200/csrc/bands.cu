@@ -352,11 +352,13 @@ struct ScatterArgs {
   int cluster;                  // CTAs per thread-block cluster (adjacent bands), 1 = no clusters
 };
 
-constexpr int SC_CAPW = 512;  // flattened entries a warp stages per round
+constexpr int SC_CAPW = 512;       // flattened entries a warp stages per round
+constexpr int SC_PRIVATE_ROWS = 256;  // bands this narrow get one accumulator copy PER WARP (32 KB)
 
 static size_t scatter_smem_bytes(int max_rows, bool spmv) {
-  return sizeof(double) * static_cast<size_t>(max_rows > 0 ? max_rows : 1) + BAND_WARPS * SC_CAPW * sizeof(int32_t) +
-         (spmv ? BAND_WARPS * SC_CAPW : 0) + 16;
+  size_t rows = static_cast<size_t>(max_rows > 0 ? max_rows : 1);
+  if (rows < static_cast<size_t>(BAND_WARPS) * SC_PRIVATE_ROWS) rows = static_cast<size_t>(BAND_WARPS) * SC_PRIVATE_ROWS;
+  return sizeof(double) * rows + BAND_WARPS * SC_CAPW * sizeof(int32_t) + (spmv ? BAND_WARPS * SC_CAPW : 0) + 16;
 }
 
 // CTA (band b, column split h).  A warp takes 32 consecutive columns of the chunk, one run descriptor
@@ -380,8 +382,15 @@ __global__ void __launch_bounds__(BAND_THREADS) band_scatter_kernel(const Scatte
     const int32_t row0 = bv.rb[b];
     const int32_t R = bv.rb[b + 1] - row0;  // an empty band still takes part in the split's barriers
     const int32_t c_lo = bv.cs[h], c_hi = bv.cs[h + 1];
+    // A narrow band is a band of POPULAR rows (bands hold equal numbers of entries): every warp step
+    // then carries several entries of the same row, and 32 warps hammering a handful of shared-memory
+    // words with CAS loops serialise.  Such bands get one accumulator copy per warp; inside a step equal
+    // rows are combined with match.any + shuffles and one lane per row does a plain add.  No atomics.
+    const bool priv = R <= SC_PRIVATE_ROWS;
+    double* wacc = acc + (priv ? warp * R : 0);
+    const unsigned lt_mask = (1u << lane) - 1u;
     __syncthreads();
-    for (int r = tid; r < R; r += BAND_THREADS) acc[r] = 0.0;
+    for (int r = tid; r < (priv ? R * BAND_WARPS : R); r += BAND_THREADS) acc[r] = 0.0;
     __syncthreads();
     // software-pipelined descriptors: the next chunk's are fetched (and its runs prefetched to L2)
     // while the current chunk is walked
@@ -477,18 +486,49 @@ __global__ void __launch_bounds__(BAND_THREADS) band_scatter_kernel(const Scatte
               xx[t] = __dmul_rn(xx[t], w);
             }
           }
+          if (priv) {
 #pragma unroll
-          for (int t = 0; t < U; ++t)
-            if (rr[t] >= 0) atomicAdd(&acc[rr[t]], xx[t]);
+            for (int t = 0; t < U; ++t) {
+              if (q0 + t * 32 >= n) break;  // warp-uniform
+              const unsigned same = __match_any_sync(0xffffffffu, rr[t] >= 0 ? rr[t] : -1 - lane);
+              // the lowest lane of each group gathers the group's values (groups are small: a row appears
+              // at most once per column)
+              double sum = xx[t];
+              unsigned rest = same & ~lt_mask & ~(1u << lane);  // members above me
+              const bool leader = (same & lt_mask) == 0u;
+              unsigned pending = __ballot_sync(0xffffffffu, leader && rest != 0u);
+              while (pending) {  // warp-uniform loop: at most (largest group - 1) rounds
+                const int src = rest ? (__ffs(rest) - 1) : lane;
+                const double v = __shfl_sync(0xffffffffu, xx[t], src);
+                if (leader && rest) {
+                  sum = __dadd_rn(sum, v);
+                  rest &= rest - 1;
+                }
+                pending = __ballot_sync(0xffffffffu, leader && rest != 0u);
+              }
+              if (leader && rr[t] >= 0) wacc[rr[t]] = __dadd_rn(wacc[rr[t]], sum);
+              __syncwarp();
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < U; ++t)
+              if (rr[t] >= 0) atomicAdd(&acc[rr[t]], xx[t]);
+          }
         }
         __syncwarp();
       }
     }
     __syncthreads();
-    if (bv.S == 1) {
-      for (int r = tid; r < R; r += BAND_THREADS) a.out[row0 + r] = acc[r];
-    } else {
-      for (int r = tid; r < R; r += BAND_THREADS) ptx::red_add_f64(a.out + row0 + r, acc[r]);
+    for (int r = tid; r < R; r += BAND_THREADS) {
+      double v = acc[r];
+      if (priv) {
+#pragma unroll
+        for (int w = 1; w < BAND_WARPS; ++w) v = __dadd_rn(v, acc[w * R + r]);  // fixed order
+      }
+      if (bv.S == 1)
+        a.out[row0 + r] = v;
+      else
+        ptx::red_add_f64(a.out + row0 + r, v);
     }
   }
 }
@@ -900,6 +940,7 @@ int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out) {
   a.out = d_out;
   if (bp->S > 1) SB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * static_cast<size_t>(m->nrow), m->stream));
   a.max_rows = (bp->max_rows > 0 ? bp->max_rows : 1);
+  if (a.max_rows < BAND_WARPS * SC_PRIVATE_ROWS) a.max_rows = BAND_WARPS * SC_PRIVATE_ROWS;  // room for the per-warp copies
   const size_t smem = scatter_smem_bytes(a.max_rows, d_v != nullptr);
   int ctas = static_cast<int>((200 * 1024) / (smem + 2048));
   if (ctas > 2) ctas = 2;

@@ -550,9 +550,16 @@ int launch_vec_div(cudaStream_t s, double* d, int64_t n, double divisor) {
 int launch_sweep(sb200_matrix* m, SweepMode mode, const double* d_v, double divisor, double* d_out) {
   if (mode == SWEEP_ROWSUM || mode == SWEEP_SPMV) SB_TRY(decide_row_path(m));
   if ((mode == SWEEP_ROWSUM || mode == SWEEP_SPMV) && m->row_path == 1) {
-    SB_TRY(launch_band_scatter(m, mode == SWEEP_SPMV ? d_v : nullptr, d_out));
-    if (mode == SWEEP_ROWSUM && divisor != 0.0) SB_TRY(launch_vec_div(m->stream, d_out, m->nrow, divisor));
-    return SB200_OK;
+    const int rc = launch_band_scatter(m, mode == SWEEP_SPMV ? d_v : nullptr, d_out);
+    if (rc == SB200_OK) {
+      if (mode == SWEEP_ROWSUM && divisor != 0.0) SB_TRY(launch_vec_div(m->stream, d_out, m->nrow, divisor));
+      return SB200_OK;
+    }
+    // the band plan could not be built for this shape (memory, row budget): not an error for the caller —
+    // the plan-free L2-atomic kernels below serve every shape.  A CUDA failure is still a failure.
+    if (rc != SB200_E_UNSUPPORTED && rc != SB200_E_NOMEM) return rc;
+    cudaGetLastError();
+    m->row_path = 0;
   }
   if (mode == SWEEP_ROWSUM || mode == SWEEP_SPMV) {
     // scatter targets start from zero (the reference's zero-initialised NumericVector, RcppSparse.h:139)
