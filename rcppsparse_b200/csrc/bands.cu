@@ -547,31 +547,41 @@ struct TransposeArgs {
   int32_t* i_out;
   double* x_out;
   int max_rows;  // R capacity of the shared-memory tables (even)
+  int cluster;   // CTAs per thread-block cluster (adjacent bands of one split kept on the same chunk), 1 = none
+  int debug;     // timing experiments only (SB200_TRANSPOSE_DEBUG): 1 = skip the result stores, 2 = skip the value loads
 };
+
+constexpr int TR_CAPW = 384;  // flattened entries of a warp's 32 columns kept in shared memory between the passes
 
 static size_t transpose_smem_bytes(int max_rows) {
   const size_t R = static_cast<size_t>(max_rows);
-  return R * 4 * 2 /* cursor, rowpos */ + R * 2 * BAND_WARPS * 2 /* cnt, rel (u16) */ + 32;
+  return R * 4 * 2 /* cursor, rowpos */ + R * 2 * BAND_WARPS * 2 /* cnt, rel (u16) */ +
+         static_cast<size_t>(BAND_WARPS) * TR_CAPW * (4 + 2 + 2) /* entry index, row, column-in-warp */ + 32;
 }
 
 __global__ void __launch_bounds__(BAND_THREADS) band_transpose_kernel(const TransposeArgs a) {
   extern __shared__ __align__(16) unsigned char tsm[];
   const BandView& bv = a.bv;
   const int MR = a.max_rows;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t* cursor = reinterpret_cast<uint32_t*>(tsm);                      // [MR] next free slot of each row
   uint32_t* rowpos = cursor + MR;                                           // [MR] slot base of the row for this chunk
   uint32_t* cntw = rowpos + MR;                                             // [WARPS*MR/2] u16 pairs: entries of (warp, row)
   uint16_t* rel = reinterpret_cast<uint16_t*>(cntw + (BAND_WARPS * MR) / 2);  // [WARPS*MR] running offset of (warp, row)
   uint16_t* cnt16 = reinterpret_cast<uint16_t*>(cntw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int32_t* flatk_all = reinterpret_cast<int32_t*>(rel + static_cast<size_t>(BAND_WARPS) * MR);  // [WARPS][CAPW]
+  uint16_t* flatr_all = reinterpret_cast<uint16_t*>(flatk_all + BAND_WARPS * TR_CAPW);
+  uint16_t* flatl_all = flatr_all + BAND_WARPS * TR_CAPW;
+  int32_t* flatk = flatk_all + warp * TR_CAPW;   // entry index of every flattened slot of my 32 columns
+  uint16_t* flatr = flatr_all + warp * TR_CAPW;  // its row inside the band (filled by pass 1)
+  uint16_t* flatl = flatl_all + warp * TR_CAPW;  // its column inside the warp's 32
   const unsigned lt_mask = (1u << lane) - 1u;
   const int units = bv.nb * bv.S;
 
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
     const int h = u / bv.nb, b = u % bv.nb;
     const int32_t row0 = bv.rb[b];
-    const int32_t R = bv.rb[b + 1] - row0;
-    if (R <= 0) continue;
+    const int32_t R = bv.rb[b + 1] - row0;  // an empty band still walks the chunks (cluster barriers)
     const int32_t c_lo = bv.cs[h], c_hi = bv.cs[h + 1];
     __syncthreads();
     for (int r = tid; r < R; r += BAND_THREADS)
@@ -579,35 +589,96 @@ __global__ void __launch_bounds__(BAND_THREADS) band_transpose_kernel(const Tran
     for (int e = tid; e < (BAND_WARPS * MR) / 2; e += BAND_THREADS) cntw[e] = 0u;
     __syncthreads();
 
+    auto count = [&](int32_t r) {
+      const int idx = warp * MR + r;
+      atomicAdd(&cntw[idx >> 1], 1u << ((idx & 1) * 16));
+    };
+    // equal rows inside a 32-entry step are ranked in lane order = source column order
+    auto place = [&](int32_t r, int32_t col, double xv) {
+      const unsigned same = __match_any_sync(0xffffffffu, r >= 0 ? r : -1 - lane);
+      if (r >= 0) {
+        const int idx = warp * MR + r;
+        const uint32_t my = rel[idx];
+        const uint32_t pos = rowpos[r] + my + __popc(same & lt_mask);
+        if (!(a.debug & 1)) {
+          a.i_out[pos] = col;
+          a.x_out[pos] = xv;
+        }
+        if ((same >> lane) == 1u) rel[idx] = static_cast<uint16_t>(my + __popc(same));  // highest lane of the group
+      }
+      __syncwarp();
+    };
+
     int32_t ns = 0, ne = 0;
     {
       const int64_t c = static_cast<int64_t>(c_lo) + tid;
-      if (c < c_hi) {
+      if (c < c_hi && R > 0) {
         ns = band_start(bv, b, c);
         ne = band_start(bv, b + 1, c);
       }
     }
     for (int64_t cbase = c_lo; cbase < c_hi; cbase += BAND_CH) {
+      if (a.cluster > 1) {
+        // adjacent bands read adjacent runs of the same columns: keep the cluster on the same chunk so
+        // HBM sees one stream per column block instead of hundreds of unrelated 32-byte reads
+        asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+      }
       const int32_t s = ns, e = ne;
       ns = ne = 0;
       {
         const int64_t c = cbase + BAND_CH + tid;
-        if (c < c_hi) {
+        if (c < c_hi && R > 0) {
           ns = band_start(bv, b, c);
           ne = band_start(bv, b + 1, c);
           for (int32_t k = ns & ~31; k < ne; k += 32) ptx::prefetch_l2(bv.i + k);
           for (int32_t k = ns & ~15; k < ne; k += 16) ptx::prefetch_l2(bv.x + k);
         }
       }
+      const int32_t len = e - s;
+      int32_t incl = len;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int32_t up = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += up;
+      }
+      const int32_t excl = incl - len;
+      const int32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      const bool cached = total <= TR_CAPW;  // warp-uniform: the common case
+      const int32_t col0 = static_cast<int32_t>(cbase) + 32 * warp;
+
       // ---- pass 1: entries per (warp, row) of this chunk (order-free) -------------------------------
-      warp_walk_runs<BAND_UNROLL, int32_t>(
-          s, e - s, lane, [&](int32_t k, int l, bool valid) { return valid ? __ldg(bv.i + k) - row0 : -1; },
-          [&](const int32_t& r) {
-            if (r >= 0) {
-              const int idx = warp * MR + r;
-              atomicAdd(&cntw[idx >> 1], 1u << ((idx & 1) * 16));
+      if (cached) {
+        // each lane expands its own run into the warp's flat list (one store per entry, no per-entry
+        // search); then 32 consecutive slots per step = consecutive entries of a run (coalesced)
+        for (int32_t j = 0; j < len; ++j) {
+          flatk[excl + j] = s + j;
+          flatl[excl + j] = static_cast<uint16_t>(lane);
+        }
+        __syncwarp();
+        for (int32_t q0 = 0; q0 < total; q0 += 32 * BAND_UNROLL) {
+          int32_t rr[BAND_UNROLL];
+#pragma unroll
+          for (int t = 0; t < BAND_UNROLL; ++t) {
+            const int32_t q = q0 + t * 32 + lane;
+            rr[t] = (q < total) ? __ldg(bv.i + flatk[q]) - row0 : -1;
+          }
+#pragma unroll
+          for (int t = 0; t < BAND_UNROLL; ++t) {
+            const int32_t q = q0 + t * 32 + lane;
+            if (rr[t] >= 0) {
+              flatr[q] = static_cast<uint16_t>(rr[t]);
+              count(rr[t]);
             }
-          });
+          }
+        }
+      } else {
+        warp_walk_runs<BAND_UNROLL, int32_t>(
+            s, len, lane, [&](int32_t k, int l, bool valid) { return valid ? __ldg(bv.i + k) - row0 : -1; },
+            [&](const int32_t& r) {
+              if (r >= 0) count(r);
+            });
+      }
       __syncthreads();
       // ---- per row: slot ranges of the 16 warps in warp (= column) order; advance the cursor ------------
       for (int r = tid; r < R; r += BAND_THREADS) {
@@ -624,32 +695,44 @@ __global__ void __launch_bounds__(BAND_THREADS) band_transpose_kernel(const Tran
         cursor[r] = base + run;
       }
       __syncthreads();
-      // ---- pass 2: place.  Equal rows inside a step are ranked in lane order = source column order ------
-      warp_walk_runs<BAND_UNROLL, PlaceItem>(
-          s, e - s, lane,
-          [&](int32_t k, int l, bool valid) {
-            PlaceItem it;
-            it.r = -1 - lane;  // unique sentinel: never matches another lane
-            it.col = static_cast<int32_t>(cbase + 32 * warp + l);
-            it.xv = 0.0;
-            if (valid) {
-              it.r = __ldg(bv.i + k) - row0;
-              it.xv = ptx::ld_stream_f64(bv.x + k);
+      // ---- pass 2: place --------------------------------------------------------------------------------
+      if (cached) {
+        for (int32_t q0 = 0; q0 < total; q0 += 32 * BAND_UNROLL) {
+          int32_t rr[BAND_UNROLL], cc[BAND_UNROLL];
+          double xx[BAND_UNROLL];
+#pragma unroll
+          for (int t = 0; t < BAND_UNROLL; ++t) {
+            const int32_t q = q0 + t * 32 + lane;
+            rr[t] = -1;
+            cc[t] = 0;
+            xx[t] = 0.0;
+            if (q < total) {
+              rr[t] = flatr[q];
+              cc[t] = col0 + flatl[q];
+              xx[t] = (a.debug & 2) ? 1.0 : ptx::ld_stream_f64(bv.x + flatk[q]);
             }
-            return it;
-          },
-          [&](const PlaceItem& it) {
-            const unsigned same = __match_any_sync(0xffffffffu, it.r);
-            if (it.r >= 0) {
-              const int idx = warp * MR + it.r;
-              const uint32_t my = rel[idx];
-              const uint32_t pos = rowpos[it.r] + my + __popc(same & lt_mask);
-              a.i_out[pos] = it.col;
-              a.x_out[pos] = it.xv;
-              if ((same >> lane) == 1u) rel[idx] = static_cast<uint16_t>(my + __popc(same));  // highest lane of the group
-            }
-            __syncwarp();
-          });
+          }
+#pragma unroll
+          for (int t = 0; t < BAND_UNROLL; ++t)
+            if (q0 + t * 32 < total) place(rr[t], cc[t], xx[t]);  // warp-uniform guard
+        }
+        __syncwarp();
+      } else {
+        warp_walk_runs<BAND_UNROLL, PlaceItem>(
+            s, len, lane,
+            [&](int32_t k, int l, bool valid) {
+              PlaceItem it;
+              it.r = -1;
+              it.col = col0 + l;
+              it.xv = 0.0;
+              if (valid) {
+                it.r = __ldg(bv.i + k) - row0;
+                it.xv = ptx::ld_stream_f64(bv.x + k);
+              }
+              return it;
+            },
+            [&](const PlaceItem& it) { place(it.r, it.col, it.xv); });
+      }
     }
   }
 }
@@ -1016,7 +1099,7 @@ int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out) {
 }
 
 // ---- transpose -------------------------------------------------------------------------------------------
-constexpr int TRANSPOSE_ROWS_CAP = 2688;  // 72 B of tables per row: one CTA per SM at the cap, two below half
+constexpr int TRANSPOSE_ROWS_CAP = 2432;  // 72 B of tables per row + 48 KB of flat lists: one CTA per SM at the cap, two when small
 
 int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double* d_x_out) {
   cudaStream_t st = m->stream;
@@ -1059,7 +1142,38 @@ int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double
     int grid = m->sm_count * ctas;
     if (grid > bp->nb * bp->S) grid = bp->nb * bp->S;
     e = cudaFuncSetAttribute(band_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e == cudaSuccess) {
+    // measured (profiles/r01): clusters of 1 / 2 / 4 adjacent bands in lockstep: scatter 34.6 / 33.0 / 39.9 ms
+    // at C3 — no gain, so off by default
+    int cluster = 1;
+    if (const char* ev = getenv("SB200_TRANSPOSE_CLUSTER")) cluster = atoi(ev);
+    while (cluster > 1 && (bp->nb % cluster != 0 || grid % cluster != 0)) cluster >>= 1;
+    if (cluster < 1) cluster = 1;
+    a.cluster = cluster;
+    a.debug = 0;
+    if (const char* ev = getenv("SB200_TRANSPOSE_DEBUG")) a.debug = atoi(ev);
+    bool launched = false;
+    if (e == cudaSuccess && cluster > 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(BAND_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cluster;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (cudaLaunchKernelEx(&cfg, band_transpose_kernel, a) == cudaSuccess) {
+        launched = true;
+        count_launch();
+      } else {
+        cudaGetLastError();  // cluster launch not possible with this footprint: free-running CTAs
+        a.cluster = 1;
+      }
+    }
+    if (e == cudaSuccess && !launched) {
       band_transpose_kernel<<<grid, BAND_THREADS, smem, st>>>(a);
       count_launch();
       e = cudaGetLastError();
