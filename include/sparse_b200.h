@@ -40,6 +40,7 @@ extern "C" {
 /* flags for sb200_matrix_create* */
 #define SB200_PIN_HOST 1u    /* cudaHostRegister i/p/x for the upload (R-owned memory), unregister after */
 #define SB200_NO_VALIDATE 2u /* skip the structure-validation kernel (trusted producer, benchmarks) */
+#define SB200_NO_ROW_PLAN 4u /* sb200_matrix_create: do not prepare the row-band plan during the upload (column sweeps only) */
 
 /* Opaque device-resident mirror of one dgCMatrix (or of one column block of it, which is
  * itself a valid dgCMatrix with the same nrow — the unit of multi-GPU sharding).

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <new>
 #include <string>
 
@@ -107,13 +108,13 @@ static int new_handle(int device, int32_t nrow, int32_t ncol, int64_t nnz, sb200
   m->nrow = nrow;
   m->ncol = ncol;
   m->nnz = nnz;
-  cudaDeviceProp prop;
-  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  int sms = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) {
     free_matrix(m);
-    return cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__);
+    return cuda_fail(e, "cudaDeviceGetAttribute", __FILE__, __LINE__);
   }
-  m->sm_count = prop.multiProcessorCount;
+  m->sm_count = sms;
   e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     free_matrix(m);
@@ -141,7 +142,9 @@ int alloc_matrix(int device, int32_t nrow, int32_t ncol, int64_t nnz, sb200_matr
   return SB200_OK;
 }
 
-int finish_matrix(sb200_matrix* m, unsigned flags) {
+// Everything the sweeps need besides i/p/x, on the handle's stream: workspace, staging vectors, structure
+// check (reads its verdict back, so it waits for p and i), tile plan.  finish_matrix() = this + a stream sync.
+static int enqueue_finish(sb200_matrix* m, unsigned flags) {
   m->ws_bytes = 16 + 4 * 1024 + 8 * 1024 + 4 * 1024;  // sweep ticket + carries, then lockstep counters
   SB_TRY(pool_alloc(&m->d_ws, m->ws_bytes, m->stream));
   SB_CUDA(cudaMemsetAsync(m->d_ws, 0, m->ws_bytes, m->stream));
@@ -151,6 +154,11 @@ int finish_matrix(sb200_matrix* m, unsigned flags) {
   SB_TRY(pool_alloc(reinterpret_cast<void**>(&m->d_stage_out), padded_bytes(sizeof(double) * static_cast<size_t>(m->stage_len)), m->stream));
   if (!(flags & SB200_NO_VALIDATE)) SB_TRY(validate_structure(m));
   SB_TRY(build_sweep_plan(m));
+  return SB200_OK;
+}
+
+int finish_matrix(sb200_matrix* m, unsigned flags) {
+  SB_TRY(enqueue_finish(m, flags));
   SB_CUDA(cudaStreamSynchronize(m->stream));
   return SB200_OK;
 }
@@ -205,17 +213,42 @@ int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int
     if (!pinned_x) pinned_x = cudaHostRegister(const_cast<double*>(x), bx, cudaHostRegisterDefault) == cudaSuccess;
     cudaGetLastError();
   }
-  cudaError_t e = cudaMemcpyAsync(m->d_p, p, bp, cudaMemcpyHostToDevice, m->stream);
+  // The value array is two thirds of the bytes and nothing at create time reads it: it goes up on a second
+  // stream while the structure check, the tile plan and (for matrices that take the banded row path) the row
+  // histogram of the band plan run on p and i behind their own, shorter copies.
+  const bool trace = getenv("SB200_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  cudaStream_t xs = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_p, p, bp, cudaMemcpyHostToDevice, m->stream);
   if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(m->d_i, i, bi, cudaMemcpyHostToDevice, m->stream);
-  if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(m->d_x, x, bx, cudaMemcpyHostToDevice, m->stream);
+  if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(m->d_x, x, bx, cudaMemcpyHostToDevice, xs);
+  int rc = SB200_OK;
+  if (e == cudaSuccess) rc = enqueue_finish(m, flags);
+  if (e == cudaSuccess && rc == SB200_OK && nnz > 0 && m->nrow > 0 && !(flags & SB200_NO_ROW_PLAN)) {
+    // plan failures here are not fatal: the row sweeps retry (or fall back to the L2 path) on first use
+    if (decide_row_path(m) == SB200_OK && m->row_path == 1) ensure_scatter_plan(m);
+    set_error("");
+  }
+  const auto t1 = std::chrono::steady_clock::now();
   if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+  const auto t2 = std::chrono::steady_clock::now();
+  if (xs) {
+    const cudaError_t ex = cudaStreamSynchronize(xs);
+    if (e == cudaSuccess) e = ex;
+    cudaStreamDestroy(xs);
+  }
   if (pinned_i) cudaHostUnregister(const_cast<int32_t*>(i));
   if (pinned_x) cudaHostUnregister(const_cast<double*>(x));
+  if (trace) {
+    const auto t3 = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "[sb200 trace] create: enqueue %.2f ms; structure stream %.2f ms; values %.2f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
+  }
   if (e != cudaSuccess) {
     free_matrix(m);
     return cuda_fail(e, "upload of i/p/x", __FILE__, __LINE__);
   }
-  const int rc = finish_matrix(m, flags);
   if (rc != SB200_OK) {
     free_matrix(m);
     return rc;
