@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-row-companion", action="store_true",
+                    help="keep rowSums/rowMeans on the scatter kernels (no row-ordered copy of the resident mirror)")
     return ap.parse_args()
 
 
@@ -68,11 +70,11 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def profile_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+def profile_traffic(kernel):
+    """dram bytes per launch of `kernel` at the default workload from the committed ncu capture, if any."""
     path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     try:
-        return json.load(open(path))["dram_bytes_per_launch"]
+        return json.load(open(path))["kernels"][kernel]["dram_bytes_per_launch"]
     except Exception:
         return None
 
@@ -269,6 +271,43 @@ def run_b200(args, ops):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- row sums of a resident mirror -------------------------------------------------------------------------
+    # The library serves rowSums/rowMeans with its scatter kernel until a mirror has been asked for them more than
+    # SB200_ROW_COMPANION_AFTER (8) times, then from a row-ordered copy of x (sparse_b200.h).  The steady state of
+    # this benchmark is the second regime; the first is timed here, with the one-off cost of the switch, so that
+    # the line carries both.
+    row_companion = None
+    if any(op in ("rowSums", "rowMeans") for op in ops):
+        out_r = torch.empty(max(D.nrow, 1), dtype=torch.float64, device=dev)
+        if args.no_row_companion:
+            D.row_companion(-1)
+        path0 = D.row_path()
+        for _ in range(2):
+            D.row_sums_dev(out_r)
+        torch.cuda.synchronize()
+        pre = []
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            D.row_sums_dev(out_r)
+            e1.record()
+            e1.synchronize()
+            pre.append(e0.elapsed_time(e1))
+        ab0 = D.algorithmic_bytes("row_sums")
+        row_companion = {"scatter_path": path0, "scatter_ms_per_call": float(np.median(pre)),
+                         "scatter_GBps": ab0 / (float(np.median(pre)) * 1e-3) / 1e9, "scatter_algorithmic_bytes": ab0,
+                         "policy": "row-ordered copy after 8 row-sum calls on a mirror that owns its arrays",
+                         "built": False}
+        if not args.no_row_companion:
+            try:
+                t0 = time.perf_counter()
+                D.row_companion(1)  # what the 9th call would do on its own; explicit so that it is timed, and so that
+                torch.cuda.synchronize()  # it precedes the warm-up whatever --warmup is
+                row_companion.update(built=True, build_ms=(time.perf_counter() - t0) * 1e3, extra_hbm_bytes=8 * nnz + 4 * (D.nrow + 1))
+            except Exception as e:
+                row_companion["error"] = f"{type(e).__name__}: {e}"
+        del out_r
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -317,14 +356,16 @@ def run_b200(args, ops):
     ms_per_step = total_ms / args.steps
     value = len(ops) * nnz_total / (ms_per_step * 1e-3)
     per_op = {}
+    on_copy = D.row_path() == "row-companion"
     for op in ops:
-        ab = D.algorithmic_bytes(ABI_OP[op])
+        ab = D.algorithmic_bytes(ABI_OP[op] + ("_companion" if on_copy and op in ("rowSums", "rowMeans") else ""))
         gbs = ab / (per_op_ms[op] * 1e-3) / 1e9
         per_op[op] = {"ms": per_op_ms[op], "ms_min": per_op_min[op], "nnz_per_s_per_gpu": nnz / (per_op_ms[op] * 1e-3),
                       "algorithmic_bytes": ab, "achieved_GBps": gbs, "frac_of_measured": gbs / peak,
                       "frac_of_nominal_8TBps": gbs / NOMINAL_HBM_GBS}
     dom = max(ops, key=lambda o: per_op_ms[o])
-    row_kernel = "band_scatter_kernel" if D.row_path() == "banded" else "rowsum_stream_kernel"
+    row_kernel = ("sweep_kernel<COLSUM> over the row-ordered copy" if on_copy else
+                  "band_scatter_kernel" if D.row_path() == "banded" else "rowsum_stream_kernel")
     dom_kernel = {"rowSums": row_kernel, "rowMeans": row_kernel, "colSums": "sweep_kernel<COLSUM>",
                   "colMeans": "sweep_kernel<COLSUM>", "spmv": "sweep_kernel<SPMV>", "spmv_t": "sweep_kernel<SPMV_T>",
                   "transpose": "transpose_band_kernel"}[dom]
@@ -333,13 +374,15 @@ def run_b200(args, ops):
                 "frac_of_nominal_8TBps": per_op[dom]["achieved_GBps"] / NOMINAL_HBM_GBS,
                 "algorithmic_bytes_per_launch": per_op[dom]["algorithmic_bytes"], "ms_per_launch": per_op_ms[dom],
                 "timed": "CUDA events on the launching stream around the op (zero-fill + kernel), mean over the timed steps",
-                "traffic": profile_traffic()}
+                "traffic": profile_traffic(dom_kernel) if (args.workload, args.scale) == ("C2", 1.0) else None}
+    if row_companion is not None:
+        row_companion["scatter_frac_of_measured"] = row_companion["scatter_GBps"] / peak
 
     line = {
         "metric": METRIC, "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(spec, args, ops, nnz), "per_op": per_op, "roofline": roofline,
-        "row_path": D.row_path(),
+        "row_path": D.row_path(), "row_companion": row_companion,
         "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
     }
 

@@ -22,7 +22,7 @@ SYMBOLS = [
     "sb200_row_sums", "sb200_col_means", "sb200_row_means", "sb200_spmv", "sb200_spmv_t", "sb200_transpose",
     "sb200_col_sums_dev", "sb200_row_sums_dev", "sb200_spmv_dev", "sb200_spmv_t_dev", "sb200_transpose_dev",
     "sb200_vec_div_dev", "sb200_launch_count", "sb200_algorithmic_bytes", "sb200_synth_create",
-    "sb200_synth_vector_dev", "sb200_matrix_download_columns", "sb200_matrix_row_path",
+    "sb200_synth_vector_dev", "sb200_matrix_download_columns", "sb200_matrix_row_path", "sb200_matrix_row_companion",
 ]
 
 
@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
         "sb200_synth_vector_dev": ([vp, u64, i64, i64, vp], C.c_int),
         "sb200_matrix_download_columns": ([vp, i64, i64, vp, vp, vp, C.POINTER(i64)], C.c_int),
         "sb200_matrix_row_path": ([vp, C.POINTER(C.c_int)], C.c_int),
+        "sb200_matrix_row_companion": ([vp, C.c_int], C.c_int),
     }
     for name in SYMBOLS:
         fn = getattr(L, name)  # AttributeError here = the .so does not export what the header declares

@@ -76,6 +76,11 @@ static void free_matrix(sb200_matrix* m) {
   // frees are ordered after the handle's own work; a caller-owned stream may be gone already
   cudaStream_t fs = m->owns_stream ? m->stream : static_cast<cudaStream_t>(0);
   if (!m->owns_stream && m->stream) cudaStreamSynchronize(m->stream), cudaGetLastError();
+  if (m->rows) {
+    m->rows->stream = m->stream;  // shares the owner's stream (owns_stream == false)
+    free_matrix(m->rows);
+    m->rows = nullptr;
+  }
   if (m->owns_arrays) {
     pool_free(m->d_i, fs);
     pool_free(m->d_p, fs);
@@ -154,6 +159,64 @@ static int enqueue_finish(sb200_matrix* m, unsigned flags) {
   SB_TRY(pool_alloc(reinterpret_cast<void**>(&m->d_stage_out), padded_bytes(sizeof(double) * static_cast<size_t>(m->stage_len)), m->stream));
   if (!(flags & SB200_NO_VALIDATE)) SB_TRY(validate_structure(m));
   SB_TRY(build_sweep_plan(m));
+  return SB200_OK;
+}
+
+int row_companion_after() {
+  static const int after = [] {
+    const char* ev = getenv("SB200_ROW_COMPANION_AFTER");
+    return ev ? atoi(ev) : 8;
+  }();
+  return after;
+}
+
+void drop_row_companion(sb200_matrix* m) {
+  if (m->rows) {
+    m->rows->stream = m->stream;
+    free_matrix(m->rows);
+    m->rows = nullptr;
+  }
+  if (m->rows_state == 1) m->rows_state = 0;
+  m->row_sum_calls = 0;
+}
+
+// Transposed copy on the owner's stream, keeping only what a row sum reads (p over rows, x in row order, the
+// tile plan).  Costs one transpose and 8 B per entry of HBM; skipped when that would not
+// leave room to spare.  Failure is not the caller's problem: the scatter kernels keep serving the mirror.
+int build_row_companion(sb200_matrix* m) {
+  if (m->rows_state == 1) return SB200_OK;
+  m->rows_state = -1;
+  if (m->nnz == 0 || m->nrow == 0) return SB200_OK;
+  size_t free_b = 0, total_b = 0;
+  const size_t need = 12ull * static_cast<size_t>(m->nnz) + 64ull * static_cast<size_t>(m->nrow);
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < 3 * need) {
+    cudaGetLastError();
+    return SB200_OK;
+  }
+  const std::string saved = t_last_error;
+  sb200_matrix* t = nullptr;
+  int rc = alloc_matrix(m->device, m->ncol, m->nrow, m->nnz, &t);
+  if (rc == SB200_OK) {
+    cudaStreamSynchronize(t->stream);  // its arrays were allocated in that stream's order
+    cudaStreamDestroy(t->stream);
+    t->stream = m->stream;
+    t->owns_stream = false;
+    t->rows_state = -1;
+    rc = transpose_device(m, t->d_p, t->d_i, t->d_x);
+    if (rc == SB200_OK) {
+      pool_free(t->d_i, m->stream);
+      t->d_i = nullptr;
+      rc = finish_matrix(t, SB200_NO_VALIDATE);
+    }
+  }
+  if (rc != SB200_OK) {
+    if (t) free_matrix(t);
+    cudaGetLastError();
+    t_last_error = saved;
+    return SB200_OK;
+  }
+  m->rows = t;
+  m->rows_state = 1;
   return SB200_OK;
 }
 
@@ -303,6 +366,7 @@ int sb200_matrix_refresh_values(sb200_matrix* m, const double* x) {
   ENTER(m);
   if (m->nnz == 0) return SB200_OK;
   if (!x) return fail(SB200_E_INVALID, "x is NULL");
+  drop_row_companion(m);  // its values are the old ones; the call count starts over
   SB_CUDA(cudaMemcpyAsync(m->d_x, x, sizeof(double) * static_cast<size_t>(m->nnz), cudaMemcpyHostToDevice, m->stream));
   SB_CUDA(cudaStreamSynchronize(m->stream));
   return SB200_OK;
@@ -363,6 +427,7 @@ int sb200_transpose_dev(sb200_matrix* m, sb200_matrix** out) {
   ENTER(m);
   sb200_matrix* t = nullptr;
   SB_TRY(alloc_matrix(m->device, m->ncol, m->nrow, m->nnz, &t));
+  cudaStreamSynchronize(t->stream);  // t's arrays were allocated in its own stream's order, written in m's
   int rc = transpose_device(m, t->d_p, t->d_i, t->d_x);
   if (rc == SB200_OK) rc = cudaStreamSynchronize(m->stream) == cudaSuccess ? SB200_OK : fail(SB200_E_CUDA, "transpose: stream sync failed");
   // the result is canonical by construction; skip re-validation
@@ -431,6 +496,7 @@ int sb200_transpose(sb200_matrix* m, int32_t* p_out, int32_t* i_out, double* x_o
   if (!p_out || (m->nnz > 0 && (!i_out || !x_out))) return fail(SB200_E_INVALID, "NULL output array");
   sb200_matrix* t = nullptr;
   SB_TRY(alloc_matrix(m->device, m->ncol, m->nrow, m->nnz, &t));
+  cudaStreamSynchronize(t->stream);  // t's arrays were allocated in its own stream's order, written in m's
   int rc = transpose_device(m, t->d_p, t->d_i, t->d_x);
   cudaError_t e = cudaSuccess;
   if (rc == SB200_OK) {
@@ -451,7 +517,23 @@ int sb200_matrix_row_path(sb200_matrix* m, int* banded) {
   ENTER(m);
   if (!banded) return fail(SB200_E_INVALID, "banded is NULL");
   SB_TRY(decide_row_path(m));
-  *banded = m->row_path;
+  *banded = m->rows_state == 1 ? 2 : m->row_path;
+  return SB200_OK;
+}
+
+int sb200_matrix_row_companion(sb200_matrix* m, int action) {
+  ENTER(m);
+  if (action > 0) {
+    if (m->rows_state != 1) {
+      m->rows_state = 0;
+      SB_TRY(build_row_companion(m));
+    }
+    if (m->rows_state != 1 && m->nnz > 0 && m->nrow > 0)
+      return fail(SB200_E_NOMEM, "row companion could not be built (memory, or the transpose does not support this shape)");
+    return SB200_OK;
+  }
+  drop_row_companion(m);
+  m->rows_state = action < 0 ? -1 : 0;
   return SB200_OK;
 }
 
@@ -465,6 +547,8 @@ int sb200_algorithmic_bytes(const sb200_matrix* m, const char* op, int64_t* byte
     *bytes = 8 * N + 4 * (n + 1) + 8 * n;
   else if (s == "row_sums" || s == "row_means")
     *bytes = 12 * N + 8 * r;
+  else if (s == "row_sums_companion" || s == "row_means_companion")  // row-ordered x once, row pointer, output
+    *bytes = 8 * N + 4 * (r + 1) + 8 * r;
   else if (s == "spmv" || s == "spmv_t")
     *bytes = 12 * N + 4 * (n + 1) + 8 * n + 8 * r;
   else if (s == "transpose")

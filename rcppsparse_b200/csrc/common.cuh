@@ -84,6 +84,12 @@ struct sb200_matrix {
   // row-band plan for the row-indexed sweeps (bands.cu); structure-only, built on first use
   sb200::BandPlan* plan_scatter;
   int row_path;  // -1 undecided, 0 plan-free L2 atomics, 1 banded (decide_row_path)
+  // Row-major companion for rowSums / rowMeans on a resident mirror (capi.cu, build_row_companion): the
+  // transposed copy's p (over rows) and x (in row order); its i is released.  Built after
+  // `row_companion_after()` row-sum calls on a mirror that owns its arrays, dropped by refresh_values.
+  sb200_matrix* rows;
+  int rows_state;     // 0 not built, 1 built, -1 never (disabled, or the build failed once)
+  int row_sum_calls;  // row-sum calls served by the scatter kernels since the last (re)build decision
 };
 
 namespace sb200 {
@@ -129,6 +135,9 @@ int ensure_scatter_plan(sb200_matrix* m);
 int decide_row_path(sb200_matrix* m);
 int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out);  // d_v null = rowSums
 void free_matrix_plans(sb200_matrix* m, cudaStream_t s);
+int build_row_companion(sb200_matrix* m);  // capi.cu; non-fatal: leaves rows_state = -1 when it cannot be built
+void drop_row_companion(sb200_matrix* m);
+int row_companion_after();                 // SB200_ROW_COMPANION_AFTER (default 8, 0 = never build on its own)
 
 // mirror.cu
 int alloc_matrix(int device, int32_t nrow, int32_t ncol, int64_t nnz, sb200_matrix** out);  // owns arrays, uninitialised

@@ -31,6 +31,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -102,6 +104,11 @@ struct SweepGeom {
 
 constexpr int SWEEP_BLOCK = SWEEP_THREADS + 32;  // 8 consumer warps + 1 producer warp
 
+// tiles with this many column ends are summed a column per lane group (sweep_kernel)
+constexpr int SEG_LANES = 8;
+constexpr int SEG_MIN_ENDS = 2;
+constexpr int SEG_MAX_ENDS = 512;
+
 // consumer-only barrier (the producer warp never joins it)
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SWEEP_THREADS) : "memory"); }
 
@@ -122,6 +129,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK) sweep_kernel(const SweepParams pr
   __shared__ StageMeta meta[STAGES];
   __shared__ double warp_sum[2][WARPS];   // double-buffered by tile parity: one barrier per tile
   __shared__ int warp_flag[2][WARPS];
+  __shared__ double seg_carry[2];         // segment-parallel tiles: sum of the column left open by the tile
   __shared__ int cta_info[4];
 
   const int tid = threadIdx.x;
@@ -235,6 +243,57 @@ __global__ void __launch_bounds__(SWEEP_BLOCK) sweep_kernel(const SweepParams pr
       consumer_sync();
     }
 
+    // ---- tiles in which many columns end: a group of SEG_LANES lanes per column ----------------------
+    // (short columns, and the row-ordered copy of a wide matrix).  The tile holds nc + 1 segments of the
+    // entry stream: columns c0 .. c0+nc-1 end here, the last segment stays open.  Each group strides over
+    // one segment, folds with shuffles and stores — ~2 instructions per entry at 100 entries per column,
+    // where the per-thread walk below spends ~40 on searches, branches and the segmented scan.
+    // (A^T v is bound by its gathers; with few, long columns the walk's all-thread sum is the shorter tail)
+    constexpr int SEG_MIN = (MODE == SWEEP_SPMV_T) ? WARPS : SEG_MIN_ENDS;
+    const bool seg_tile = REDUCES && mt.nc >= SEG_MIN && mt.nc <= SEG_MAX_ENDS;
+    if (seg_tile) {
+      auto sum_segments = [&](auto lanes_c) {
+        constexpr int L = decltype(lanes_c)::value;
+        constexpr int GROUPS = THREADS / L;
+        const int gidx = tid / L, gl = tid % L;
+        const int nseg = mt.nc + 1;
+        for (int base = 0; base < nseg; base += GROUPS) {  // trip count uniform over the CTA
+          const int c = base + gidx;
+          double sacc = 0.0;
+          if (c < nseg) {
+            const int beg = (c == 0) ? 0 : as[c - 1] - mt.k0;
+            const int end = (c == mt.nc) ? mt.nk : as[c] - mt.k0;
+            double a0 = 0.0, a1 = 0.0;
+            int k = beg + gl;
+            for (; k + L < end; k += 2 * L) {
+              a0 = __dadd_rn(a0, xs[k]);
+              a1 = __dadd_rn(a1, xs[k + L]);
+            }
+            if (k < end) a0 = __dadd_rn(a0, xs[k]);
+            sacc = __dadd_rn(a0, a1);
+          }
+#pragma unroll
+          for (int off = L / 2; off > 0; off >>= 1) sacc = __dadd_rn(sacc, __shfl_xor_sync(0xffffffffu, sacc, off));
+          if (gl == 0 && c < nseg) {
+            if (c < mt.nc)
+              prm.out[mt.c0 + c] = (c == 0) ? __dadd_rn(cta_carry, sacc) : sacc;  // earlier CTAs' shares: fix-up below
+            else
+              seg_carry[buf] = sacc;
+          }
+        }
+      };
+      if (mt.nc < WARPS)
+        sum_segments(std::integral_constant<int, 32>{});  // a warp per column: at most one round
+      else
+        sum_segments(std::integral_constant<int, SEG_LANES>{});
+      if (MODE == SWEEP_SPMV_T) ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty_bar[s]);
+      consumer_sync();
+      cta_carry = seg_carry[buf];
+      continue;
+    }
+
     // ---- per-thread merge-path walk ------------------------------------------------------------
     int d_lo = tid * IPT;
     if (d_lo > items) d_lo = items;
@@ -282,21 +341,25 @@ __global__ void __launch_bounds__(SWEEP_BLOCK) sweep_kernel(const SweepParams pr
       if (IPT & 1) a0 = __dadd_rn(a0, xs[ki + IPT - 1]);
       acc = __dadd_rn(a0, a1);
     } else {
-#pragma unroll 1
-      for (int it = 0; it < n_my; ++it) {
-        if (ki < col_end) {
-          acc = __dadd_rn(acc, xs[ki]);
-          ++ki;
-        } else {
-          if (first_ci < 0) {
-            first_ci = ci;
-            head = acc;
+      // a column ends among my items (short columns; the row-ordered copy of a wide matrix): straight-line
+      // adds, the rare end handled in place — the rest of the warp waits for this path, so it is unrolled
+#pragma unroll
+      for (int it = 0; it < IPT; ++it) {
+        if (it < n_my) {
+          if (ki < col_end) {
+            acc = __dadd_rn(acc, xs[ki]);
+            ++ki;
           } else {
-            prm.out[mt.c0 + ci] = acc;  // began and ended inside this thread
+            if (first_ci < 0) {
+              first_ci = ci;
+              head = acc;
+            } else {
+              prm.out[mt.c0 + ci] = acc;  // began and ended inside this thread
+            }
+            acc = 0.0;
+            ++ci;
+            col_end = as[ci] - mt.k0;
           }
-          acc = 0.0;
-          ++ci;
-          col_end = as[ci] - mt.k0;
         }
       }
     }
@@ -548,6 +611,19 @@ int launch_vec_div(cudaStream_t s, double* d, int64_t n, double divisor) {
 }
 
 int launch_sweep(sb200_matrix* m, SweepMode mode, const double* d_v, double divisor, double* d_out) {
+  if (mode == SWEEP_ROWSUM && m->nnz > 0 && m->nrow > 0) {
+    // A mirror whose row sums keep being asked for gets a row-major copy of its values: from then on a row
+    // sum is the same streaming segmented sweep as a column sum (8 B per entry, no atomics) instead of a
+    // scatter.  Same arithmetic every call — only the layout is kept, like the band plan.
+    if (m->rows_state == 0 && m->owns_arrays) {
+      const int after = row_companion_after();
+      if (after > 0 && ++m->row_sum_calls > after) build_row_companion(m);
+    }
+    if (m->rows_state == 1) {
+      m->rows->stream = m->stream;
+      return launch_sweep(m->rows, SWEEP_COLSUM, nullptr, divisor, d_out);
+    }
+  }
   if (mode == SWEEP_ROWSUM || mode == SWEEP_SPMV) SB_TRY(decide_row_path(m));
   if ((mode == SWEEP_ROWSUM || mode == SWEEP_SPMV) && m->row_path == 1) {
     const int rc = launch_band_scatter(m, mode == SWEEP_SPMV ? d_v : nullptr, d_out);

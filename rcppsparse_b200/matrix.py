@@ -125,10 +125,15 @@ class DeviceMatrix:
         return n.value
 
     def row_path(self) -> str:
-        """'banded' or 'l2-atomics': which kernel serves rowSums / rowMeans / A v for this matrix."""
+        """'banded' or 'l2-atomics': which kernel serves rowSums / rowMeans / A v for this matrix;
+        'row-companion' once rowSums / rowMeans run on the row-ordered copy (A v keeps the scatter kernel)."""
         b = C.c_int()
         check(_lib.lib().sb200_matrix_row_path(self._h, C.byref(b)))
-        return "banded" if b.value else "l2-atomics"
+        return ("l2-atomics", "banded", "row-companion")[b.value]
+
+    def row_companion(self, action: int = 1) -> None:
+        """1 build the row-ordered copy now, 0 drop it, -1 drop and never build (sparse_b200.h)."""
+        check(_lib.lib().sb200_matrix_row_companion(self._h, int(action)))
 
     def refresh_values(self, x) -> None:
         check(_lib.lib().sb200_matrix_refresh_values(self._h, _ptr(x)))

@@ -279,6 +279,69 @@ def test_pinned_upload_path_and_row_path_report():
         assert D.row_path() == "banded"  # few rows: popular rows would serialise the L2 atomics
 
 
+@pytest.mark.parametrize("name", ["C1", "pl_rows5", "C2s"])
+def test_row_companion_parity_and_lifecycle(name):
+    """rowSums / rowMeans from the row-ordered copy of a resident mirror (sparse_b200.h,
+    sb200_matrix_row_companion) against the reference, and the copy's lifecycle: built on request or after
+    SB200_ROW_COMPANION_AFTER (default 8) row-sum calls, dropped by refresh_values, never built on its own
+    for adopted device arrays."""
+    spec = {"C1": synth.config("C1"), "pl_rows5": synth.powerlaw_spec(7000, 2000, 80.0, 9, row_levels=5),
+            "C2s": synth.config("C2", 0.02)}[name]
+    i, p, x = synth.generate_host(spec)
+    args = (i, p, x, spec.nrow, spec.ncol)
+    chk = oracle.best()
+    with DeviceMatrix.from_host(i, p, x, spec.nrow, spec.ncol) as D:
+        before = D.row_path()
+        assert before in ("banded", "l2-atomics")
+        D.row_companion(1)
+        assert D.row_path() == "row-companion"
+        oracle.assert_within("rowSums", D.row_sums(), chk.rowSums(*args), *args, tol=TOL)
+        oracle.assert_within("rowMeans", D.row_means(), chk.rowMeans(*args), *args, tol=TOL)
+        v = synth.dense_vector(3, spec.ncol)
+        oracle.assert_within("spmv", D.spmv(v), chk.spmv(*args, v), *args, v=v, tol=TOL)  # unaffected
+        x2 = x * -0.5 + 1.0
+        D.refresh_values(x2)
+        assert D.row_path() == before
+        args2 = (i, p, x2, spec.nrow, spec.ncol)
+        for _ in range(8):
+            oracle.assert_within("rowSums", D.row_sums(), chk.rowSums(*args2), *args2, tol=TOL)
+        assert D.row_path() == before
+        oracle.assert_within("rowMeans", D.row_means(), chk.rowMeans(*args2), *args2, tol=TOL)  # ninth call builds
+        assert D.row_path() == "row-companion"
+        oracle.assert_within("rowSums", D.row_sums(), chk.rowSums(*args2), *args2, tol=TOL)
+        D.row_companion(-1)
+        assert D.row_path() == before
+        for _ in range(10):
+            D.row_sums()
+        assert D.row_path() == before
+        oracle.assert_within("rowSums", D.row_sums(), chk.rowSums(*args2), *args2, tol=TOL)
+    import torch
+
+    di, dp, dx = (torch.from_numpy(a).cuda() for a in (i, p, x))
+    with DeviceMatrix.adopt(di, dp, dx, spec.nrow, spec.ncol) as A:
+        out = torch.empty(spec.nrow, dtype=torch.float64, device="cuda")
+        for _ in range(12):
+            A.row_sums_dev(out)
+        assert A.row_path() != "row-companion"  # the caller may rewrite dx behind the mirror
+        dx.mul_(2.0)
+        A.row_sums_dev(out)
+        torch.cuda.synchronize()
+        oracle.assert_within("rowSums", out.cpu().numpy(), 2.0 * chk.rowSums(*args), i, p, 2.0 * x, spec.nrow, spec.ncol, tol=TOL)
+
+
+def test_row_companion_golden_edges(golden):
+    """The row-ordered copy on the golden fixtures (empty rows/columns, NaN/Inf, 0-dimension shapes)."""
+    g = golden
+    args = (g["i"], g["p"], g["x"], g["nrow"], g["ncol"])
+    with DeviceMatrix.from_host(*args) as D:
+        D.row_companion(1)  # a no-op for shapes without entries or rows
+        if len(g["x"]) and g["nrow"]:
+            assert D.row_path() == "row-companion"
+        for _ in range(2):
+            oracle.assert_within("rowSums", D.row_sums(), g["rowSums"], *args, tol=TOL)
+            oracle.assert_within("rowMeans", D.row_means(), g["rowMeans"], *args, tol=TOL)
+
+
 def test_two_mirrors_and_interleaved_ops_do_not_interfere():
     a, b = synth.config("C1"), synth.powerlaw_spec(7000, 2000, 80.0, 9, row_levels=5)
     ia, pa, xa = synth.generate_host(a)

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--companion", type=int, default=0, help="1: build the row-ordered copy first, -1: never build it")
     a = ap.parse_args()
     import torch
 
@@ -40,6 +41,8 @@ def main():
     spec = synth.config(a.workload, a.scale)
     D = DeviceMatrix.synth(spec)
     D.set_stream(torch.cuda.current_stream().cuda_stream)
+    if a.companion:
+        D.row_companion(a.companion)
     dev = torch.device("cuda", 0)
     out_c = torch.empty(max(D.ncol, 1), dtype=torch.float64, device=dev)
     out_r = torch.empty(max(D.nrow, 1), dtype=torch.float64, device=dev)
@@ -78,7 +81,7 @@ def main():
             e1.record()
             e1.synchronize()
             ms.append(e0.elapsed_time(e1))
-        ab = D.algorithmic_bytes(ABI[op])
+        ab = D.algorithmic_bytes(ABI[op] + ("_companion" if op in ("rowSums", "rowMeans") and D.row_path() == "row-companion" else ""))
         best, med = float(np.min(ms)), float(np.median(ms))
         print(json.dumps({"tag": a.tag, "cfg": os.environ.get("SB200_SWEEP_CFG", ""), "workload": spec.name, "op": op, "row_path": D.row_path(),
                           "nnz": D.nnz, "ms_best": round(best, 4), "ms_median": round(med, 4),
