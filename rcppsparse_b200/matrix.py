@@ -150,22 +150,27 @@ class DeviceMatrix:
         return i, p, x
 
     # ---- host-buffer sweeps (what the C++ header calls) --------------------------------------------------
-    def _host_vec(self, fn, n):
-        out = np.empty(n, np.float64)
+    def _host_vec(self, fn, n, out=None):
+        """out: optional caller-owned result buffer (float64 numpy array or pinned torch CPU tensor of n entries),
+        as in the C ABI; a fresh numpy array otherwise."""
+        if out is None:
+            out = np.empty(n, np.float64)
+        elif int(out.shape[0]) != n or (isinstance(out, np.ndarray) and (out.dtype != np.float64 or not out.flags.c_contiguous)):
+            raise ValueError(f"out must be a contiguous float64 buffer of {n} entries")
         check(fn(self._h, _ptr(out)))
         return out
 
-    def col_sums(self):
-        return self._host_vec(_lib.lib().sb200_col_sums, self.ncol)
+    def col_sums(self, out=None):
+        return self._host_vec(_lib.lib().sb200_col_sums, self.ncol, out)
 
-    def row_sums(self):
-        return self._host_vec(_lib.lib().sb200_row_sums, self.nrow)
+    def row_sums(self, out=None):
+        return self._host_vec(_lib.lib().sb200_row_sums, self.nrow, out)
 
-    def col_means(self):
-        return self._host_vec(_lib.lib().sb200_col_means, self.ncol)
+    def col_means(self, out=None):
+        return self._host_vec(_lib.lib().sb200_col_means, self.ncol, out)
 
-    def row_means(self):
-        return self._host_vec(_lib.lib().sb200_row_means, self.nrow)
+    def row_means(self, out=None):
+        return self._host_vec(_lib.lib().sb200_row_means, self.nrow, out)
 
     def spmv(self, v):
         v = np.ascontiguousarray(v, np.float64)

@@ -61,6 +61,11 @@ def test_c2_full_size_against_the_reference_oracle():
         ri, rp, rx = chk.transpose(*args)
         assert np.array_equal(tp, rp) and np.array_equal(ti, ri)
         assert np.array_equal(tx.view(np.uint64), rx.view(np.uint64))
+        # the row sums of a resident mirror move to its row-ordered copy (sparse_b200.h): same bar
+        D.row_companion(1)
+        assert D.row_path() == "row-companion"
+        oracle.assert_within("rowSums", D.row_sums(), chk.rowSums(*args), *args, tol=TOL)
+        oracle.assert_within("rowMeans", D.row_means(), chk.rowMeans(*args), *args, tol=TOL)
 
 
 def _transpose_properties(spec, n_sample_rows=48):
@@ -96,6 +101,12 @@ def _transpose_properties(spec, n_sample_rows=48):
         A.sync(), T.sync()
         feed = abs_row_feed(A, ai, ax)
         assert bool(((rs - cs).abs() <= 2 * TOL * feed).all())
+        A.row_companion(1)  # and from A's own row-ordered copy
+        rs2 = dev_vec(A.nrow)
+        A.row_sums_dev(rs2)
+        A.sync()
+        assert A.row_path() == "row-companion" and bool(((rs2 - cs).abs() <= 2 * TOL * feed).all())
+        A.row_companion(0)
         v = dev_vec(A.ncol)
         A.synth_vector_dev(spec.seed, 0, A.ncol, v)
         y1, y2 = dev_vec(A.nrow), dev_vec(A.nrow)

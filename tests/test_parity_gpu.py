@@ -342,6 +342,27 @@ def test_row_companion_golden_edges(golden):
             oracle.assert_within("rowMeans", D.row_means(), g["rowMeans"], *args, tol=TOL)
 
 
+def test_host_ops_write_into_caller_buffers():
+    """The C ABI writes results through the caller's pointer; the Python mirror exposes that as out=."""
+    import torch
+
+    spec = synth.config("C1")
+    i, p, x = synth.generate_host(spec)
+    args = (i, p, x, spec.nrow, spec.ncol)
+    chk = oracle.best()
+    with DeviceMatrix.from_host(*args) as D:
+        buf = np.full(spec.nrow, -1.0)
+        assert D.row_sums(out=buf) is buf
+        oracle.assert_within("rowSums", buf, chk.rowSums(*args), *args, tol=TOL)
+        pinned = torch.empty(spec.ncol, dtype=torch.float64).pin_memory()
+        D.col_means(out=pinned)
+        oracle.assert_within("colMeans", pinned.numpy(), chk.colMeans(*args), *args, tol=TOL)
+        with pytest.raises(ValueError):
+            D.col_sums(out=np.empty(spec.ncol + 1))
+        with pytest.raises(ValueError):
+            D.col_sums(out=np.empty(spec.ncol, np.float32))
+
+
 def test_two_mirrors_and_interleaved_ops_do_not_interfere():
     a, b = synth.config("C1"), synth.powerlaw_spec(7000, 2000, 80.0, 9, row_levels=5)
     ia, pa, xa = synth.generate_host(a)
