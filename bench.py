@@ -57,6 +57,11 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--exchange", default=None, choices=["p2p", "nccl"],
+                    help="N > 1: the library's peer-memory exchange kernels (default) or NCCL collectives")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N > 1 with --exchange nccl: leave each op's collective in flight under the next op's sweep "
+                         "(measured slower: the NCCL kernel waits for SM resources behind the persistent sweep)")
     ap.add_argument("--no-row-companion", action="store_true",
                     help="keep rowSums/rowMeans on the scatter kernels (no row-ordered copy of the resident mirror)")
     return ap.parse_args()
@@ -248,23 +253,42 @@ def run_b200(args, ops):
     nnz = D.nnz
     local = shard.GpuLocal(D)  # binds the handle to torch's current stream
     bounds = [k * spec.ncol for k in range(world + 1)]
-    S = shard.ShardedMatrix(local, bounds, rank, device=dev)
+    S = shard.ShardedMatrix(local, bounds, rank, device=dev, exchange=args.exchange)
     v_col = torch.empty(S.ncol, dtype=torch.float64, device=dev)
     v_row = torch.empty(S.nrow, dtype=torch.float64, device=dev)
     D.synth_vector_dev(spec.seed, 0, S.ncol, v_col)
     D.synth_vector_dev(spec.seed + 7, 0, S.nrow, v_row)
     T_keep = []
 
+    # p2p: the exchange kernels of op k run on the window's stream beside the sweep of op k+1 (always);
+    # nccl: only with --overlap (measured slower: the NCCL kernel waits for SM resources behind the sweep)
+    overlap = world > 1 and (S.exchange == "p2p" or args.overlap)
+
     def run_op(op):
+        """Launch op; with more than one rank its collective is left in flight (async NCCL) so that the next
+        op's sweep overlaps it — every step waits for all of its results before it ends."""
         if op == "spmv":
-            return S.spmv(v_col)
+            return S.spmv(v_col, async_op=overlap)
         if op == "spmv_t":
-            return S.spmv_t(v_row)
+            return S.spmv_t(v_row, async_op=overlap)
         if op == "transpose":
             T_keep.clear()
-            T_keep.append(D.transpose_dev())  # local block only (sharded transpose exchange: next round)
+            T_keep.append(D.transpose_dev())  # local block only (the sharded exchange is ShardedMatrix.transpose)
             return None
-        return getattr(S, op)()
+        return getattr(S, op)(async_op=overlap)
+
+    def run_step(marks=None):
+        pend = []
+        for k, op in enumerate(ops):
+            pend.append(run_op(op))
+            if marks is not None:
+                marks[k + 1].record()
+        if overlap:
+            for r in pend:
+                if r is not None:
+                    r.wait()
+        if marks is not None:
+            marks[len(ops) + 1].record()
 
     def barrier():
         if world > 1:
@@ -312,21 +336,18 @@ def run_b200(args, ops):
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
-        for op in ops:
-            run_op(op)
+        run_step()
     barrier()
     if rank == 0:
         sampler.wait_first_sample()
     launches0 = _lib.lib().sb200_launch_count()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(ops) + 1)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(ops) + 2)] for _ in range(args.steps)]
     barrier()
     sampler.mark_begin()
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
         ev[s][0].record()
-        for k, op in enumerate(ops):
-            run_op(op)
-            ev[s][k + 1].record()
+        run_step(ev[s])
     barrier()
     t_wall = time.perf_counter() - t_wall0
     sampler.mark_end()
@@ -347,6 +368,8 @@ def run_b200(args, ops):
         dist.all_reduce(nnz_all, op=dist.ReduceOp.SUM)
     nnz_total = int(nnz_all.item())
 
+    if world > 1:
+        S.close()  # raises if an exchange barrier ever timed out
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -383,6 +406,11 @@ def run_b200(args, ops):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(spec, args, ops, nnz), "per_op": per_op, "roofline": roofline,
         "row_path": D.row_path(), "row_companion": row_companion,
+        "exchange": (None if world == 1 else
+                     "libsparse_b200 kernels over NVLink peer memory (cudaIpc window): P2P stores of each rank's slice for "
+                     "column results, rank-ordered P2P reduction for row results, flag barriers; op k's exchange runs beside op k+1's "
+                     "sweep, every result is waited for before its step ends" if S.exchange == "p2p" else
+                     "NCCL all-gather / all-reduce" + (", left in flight under the next op's sweep" if overlap else "")),
         "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
     }
 

@@ -127,6 +127,33 @@ int sb200_matrix_row_path(sb200_matrix* m, int* banded);
  * promises to call this again, or refresh, after changing values), 0 = drop, -1 = drop and never build. */
 int sb200_matrix_row_companion(sb200_matrix* m, int action);
 
+/* ---- cross-GPU exchange for column-sharded matrices (one process per GPU, GPUs of one node) ---------
+ * The reference is single-process; a column-sharded deployment needs two exchange steps:
+ * assembling column-indexed results from disjoint slices, and summing full-length row-indexed partials.
+ * Both run as this library's kernels over NVLink peer memory.  Each rank creates a window of device memory,
+ * the 64-byte handles are exchanged by the host side (any transport; rcppsparse_b200/shard.py uses
+ * torch.distributed), every rank connects, and result vectors are placed INSIDE the window (offsets in
+ * bytes from the window base, 16-byte aligned, at or after *data_offset).  Every rank must issue the same
+ * sequence of gather / reduce / barrier calls.  All calls are asynchronous on the given stream. */
+typedef struct sb200_exchange sb200_exchange;
+int sb200_exchange_create(int device, int64_t data_bytes, sb200_exchange** out, void* ipc_handle_out /* 64 bytes */);
+int sb200_exchange_connect(sb200_exchange* x, int rank, int world, const void* all_handles /* world x 64 bytes, by rank */);
+int sb200_exchange_destroy(sb200_exchange* x);
+int sb200_exchange_window(const sb200_exchange* x, void** base, int64_t* data_offset, int64_t* bytes);
+/* Column-indexed result: this rank has written doubles [slice_begin, slice_begin+slice_len) of the vector at
+ * full_offset in ITS window; copy them to the same place in every peer's window and wait until every
+ * rank's slice has landed here. */
+int sb200_exchange_gather(sb200_exchange* x, void* cuda_stream, int64_t full_offset, int64_t slice_begin, int64_t slice_len);
+/* Row-indexed result: every rank holds an n-vector of partial sums at partial_offset of its window; on return
+ * (in stream order) the vector at result_offset of EVERY window holds their sum, added in rank order (bit-
+ * identical on all ranks and run to run), divided by divisor when divisor != 0 (rowMeans: the global ncol,
+ * RcppSparse.h:154). partial and result must not overlap. */
+int sb200_exchange_reduce(sb200_exchange* x, void* cuda_stream, int64_t partial_offset, int64_t result_offset, int64_t n,
+                          double divisor);
+int sb200_exchange_barrier(sb200_exchange* x, void* cuda_stream);
+/* Synchronises the device; SB200_E_CUDA if a barrier gave up waiting for a peer (~4 s). */
+int sb200_exchange_status(sb200_exchange* x);
+
 /* ---- introspection for benchmarks ----------------------------------------------------------
  * Number of kernel launches this library has issued in this process (all handles). */
 int64_t sb200_launch_count(void);

@@ -23,6 +23,8 @@ SYMBOLS = [
     "sb200_col_sums_dev", "sb200_row_sums_dev", "sb200_spmv_dev", "sb200_spmv_t_dev", "sb200_transpose_dev",
     "sb200_vec_div_dev", "sb200_launch_count", "sb200_algorithmic_bytes", "sb200_synth_create",
     "sb200_synth_vector_dev", "sb200_matrix_download_columns", "sb200_matrix_row_path", "sb200_matrix_row_companion",
+    "sb200_exchange_create", "sb200_exchange_connect", "sb200_exchange_destroy", "sb200_exchange_window",
+    "sb200_exchange_gather", "sb200_exchange_reduce", "sb200_exchange_barrier", "sb200_exchange_status",
 ]
 
 
@@ -81,6 +83,14 @@ def lib() -> C.CDLL:
         "sb200_matrix_download_columns": ([vp, i64, i64, vp, vp, vp, C.POINTER(i64)], C.c_int),
         "sb200_matrix_row_path": ([vp, C.POINTER(C.c_int)], C.c_int),
         "sb200_matrix_row_companion": ([vp, C.c_int], C.c_int),
+        "sb200_exchange_create": ([C.c_int, i64, pp, vp], C.c_int),
+        "sb200_exchange_connect": ([vp, C.c_int, C.c_int, vp], C.c_int),
+        "sb200_exchange_destroy": ([vp], C.c_int),
+        "sb200_exchange_window": ([vp, pp, C.POINTER(i64), C.POINTER(i64)], C.c_int),
+        "sb200_exchange_gather": ([vp, vp, i64, i64, i64], C.c_int),
+        "sb200_exchange_reduce": ([vp, vp, i64, i64, i64, dbl], C.c_int),
+        "sb200_exchange_barrier": ([vp, vp], C.c_int),
+        "sb200_exchange_status": ([vp], C.c_int),
     }
     for name in SYMBOLS:
         fn = getattr(L, name)  # AttributeError here = the .so does not export what the header declares

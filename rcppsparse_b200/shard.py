@@ -16,6 +16,8 @@ slice bookkeeping, the collectives — is testable at world_size 2 without a GPU
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
 from typing import Protocol, Sequence
 
 import numpy as np
@@ -104,12 +106,109 @@ class GpuLocal:
         return p, i, x
 
 
+class PeerWindow:
+    """A rank's window of device memory mapped by every rank of the node (libsparse_b200's exchange layer,
+    sparse_b200.h): result vectors of a ShardedMatrix live inside it and the two exchange steps of the path are
+    the library's own kernels over NVLink peer memory — P2P stores of a rank's slice for column-indexed results,
+    a rank-ordered P2P reduction of the partials for row-indexed ones — instead of NCCL calls.
+    torch.distributed only carries the 64-byte handles (and agrees on whether every rank could connect)."""
+
+    def __init__(self, device: torch.device, rank: int, world: int, data_bytes: int, group=None):
+        from . import _lib
+        self._lib, self.device, self.rank, self.world = _lib, device, rank, world
+        self._h = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        _lib.check(_lib.lib().sb200_exchange_create(device.index, int(data_bytes) + 4096, C.byref(self._h), handle))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bytes(handle), group=group)
+        blob = b"".join(gathered)
+        rc = _lib.lib().sb200_exchange_connect(self._h, rank, world, blob)
+        err = _lib.lib().sb200_last_error().decode(errors="replace") if rc != 0 else ""
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:  # some rank could not map its peers: nobody uses the window
+            self.close()
+            raise RuntimeError(f"peer window not available on every rank (rank {rank}: {err or 'ok'})")
+        base, off, nbytes = C.c_void_p(), C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().sb200_exchange_window(self._h, C.byref(base), C.byref(off), C.byref(nbytes)))
+        self.base, self._cursor, self.bytes = base.value, off.value, nbytes.value
+        self.side = None
+
+    def alloc(self, n: int):
+        """(byte offset, float64 tensor of n entries) inside the window; 256-byte aligned."""
+        off = self._cursor
+        need = max(int(n), 1) * 8
+        if off + need > self.bytes:
+            raise MemoryError("peer window exhausted")
+        self._cursor = (off + need + 255) & ~255
+        t = torch.as_tensor(_CudaView(self.base + off, max(int(n), 1), "<f8"), device=self.device)[:n]
+        return off, t
+
+    # Exchange kernels run on the window's own high-priority stream, ordered after the caller's current stream
+    # at the time of the call; each call returns the event that marks its completion.  They are a few small CTAs
+    # without shared memory, so they run beside the next sweep (whose persistent CTAs fill the SMs' shared
+    # memory but not their thread slots) instead of behind it; every rank issues them in the same order on
+    # that one stream, which is what the epoch barriers need.
+    def _run(self, launch) -> torch.cuda.Event:
+        if self.side is None:
+            self.side = torch.cuda.Stream(self.device, priority=-1)
+        self.side.wait_stream(torch.cuda.current_stream(self.device))
+        self._lib.check(launch(C.c_void_p(self.side.cuda_stream)))
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        return ev
+
+    def gather(self, full_off: int, slice_begin: int, slice_len: int) -> torch.cuda.Event:
+        return self._run(lambda st: self._lib.lib().sb200_exchange_gather(self._h, st, full_off, slice_begin, slice_len))
+
+    def reduce(self, partial_off: int, result_off: int, n: int, divisor: float = 0.0) -> torch.cuda.Event:
+        return self._run(lambda st: self._lib.lib().sb200_exchange_reduce(self._h, st, partial_off, result_off, n, divisor))
+
+    def barrier(self) -> torch.cuda.Event:
+        return self._run(lambda st: self._lib.lib().sb200_exchange_barrier(self._h, st))
+
+    def status(self) -> None:
+        """Synchronises; raises if a barrier gave up on a peer."""
+        self._lib.check(self._lib.lib().sb200_exchange_status(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.lib().sb200_exchange_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class Pending:
+    """Result of a sweep whose collective may still be in flight (``async_op=True``): ``wait()`` orders the
+    caller's current stream after it, applies what has to follow the collective (the mean's division) and
+    returns the full vector.  The sweep of the next op can be launched before ``wait()``: its kernel and
+    this op's collective then overlap, as in ``torch.distributed``'s own ``async_op``."""
+
+    def __init__(self, tensor, works=(), finish=None):
+        self.tensor = tensor
+        self._works = [w for w in works if w is not None]
+        self._finish = finish
+
+    def wait(self) -> torch.Tensor:
+        for w in self._works:
+            w.wait()
+        self._works = []
+        if self._finish is not None:
+            self._finish()
+            self._finish = None
+        return self.tensor
+
+
 class ShardedMatrix:
     """The reference's Matrix methods (RcppSparse.h:131-156 + the SpMV idiom) over a column-sharded matrix.
     Every method returns the FULL result vector on every rank — as a view of an internal buffer that
-    the next call of the same kind (column- or row-indexed) overwrites: clone it to keep it."""
+    the next call of the SAME method overwrites: clone it to keep it.  With ``async_op=True`` a method
+    returns a ``Pending`` instead; wait for it before calling the same method again."""
 
-    def __init__(self, local: LocalSweeps, bounds: Sequence[int], rank: int, group=None, device=None):
+    def __init__(self, local: LocalSweeps, bounds: Sequence[int], rank: int, group=None, device=None,
+                 exchange: str | None = None):
+        """exchange: "p2p" (the library's kernels over a PeerWindow; CUDA ranks of one node), "nccl"/"gloo"
+        (torch.distributed collectives), default: SB200_EXCHANGE or "p2p" on CUDA with more than one rank.
+        Construction is collective when the window is used (handles are exchanged)."""
         self.local = local
         self.bounds = list(bounds)
         self.world = len(self.bounds) - 1
@@ -123,58 +222,151 @@ class ShardedMatrix:
         self.device = device if device is not None else torch.device("cpu")
         self._counts = [self.bounds[k + 1] - self.bounds[k] for k in range(self.world)]
         self._even = len(set(self._counts)) == 1
-        self._col_full = torch.empty(self.ncol, dtype=torch.float64, device=self.device)
-        self._row_full = torch.empty(self.nrow, dtype=torch.float64, device=self.device)
+        self._bufs: dict[str, torch.Tensor] = {}
+        self.window = None
+        self._xbuf: dict[str, list] = {}
+        self._inflight: dict[str, Pending] = {}
+        want = exchange or os.environ.get("SB200_EXCHANGE") or ("p2p" if self.device.type == "cuda" and self.world > 1 else "collective")
+        if want == "p2p" and self.world > 1:
+            if self.device.type != "cuda":
+                raise ValueError("exchange='p2p' needs CUDA ranks")
+            pad = 256
+            data = 3 * 2 * (8 * self.ncol + pad) + 3 * 3 * (8 * self.nrow + pad)
+            try:
+                self.window = PeerWindow(self.device, rank, self.world, data, group)
+            except RuntimeError as e:  # raised on EVERY rank or on none (the ranks agree inside PeerWindow)
+                if exchange == "p2p" or os.environ.get("SB200_EXCHANGE") == "p2p":
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable, using torch.distributed collectives: {e}")
+        self.exchange = "p2p" if self.window is not None else "collective"
+
+    def close(self) -> None:
+        if self.window is not None:
+            self.window.status()
+            dist.barrier(group=self.group)  # nobody unmaps while a peer may still write
+            self.window.close()
+            self.window = None
+
+    # ---- p2p path: results live in the window ------------------------------------------------------------------
+    def _window_cols(self, name: str):
+        """(offset, tensor) of the result buffer to fill now: two per method, alternating — a peer that is one
+        call ahead pushes its slice into the other one, never into the result the caller still holds."""
+        st = self._xbuf.get(name)
+        if st is None:
+            st = self._xbuf[name] = [0, self.window.alloc(self.ncol), self.window.alloc(self.ncol)]
+        st[0] ^= 1
+        return st[1 + st[0]]
+
+    def _window_rows(self, name: str):
+        """((partial offset, tensor), (result offset, tensor)): one partial, two alternating results."""
+        st = self._xbuf.get(name)
+        if st is None:
+            st = self._xbuf[name] = [0, self.window.alloc(self.nrow), self.window.alloc(self.nrow), self.window.alloc(self.nrow)]
+        st[0] ^= 1
+        return st[1], st[2 + st[0]]
+
+    def _p2p_pending(self, name: str, tensor: torch.Tensor, ev: torch.cuda.Event) -> Pending:
+        p = Pending(tensor, finish=lambda: torch.cuda.current_stream(self.device).wait_event(ev))
+        self._inflight[name] = p
+        return p
+
+    def _p2p_cols(self, name: str, launch) -> Pending:
+        prev = self._inflight.pop(name, None)
+        if prev is not None:
+            prev.wait()  # the previous call of this method must have landed before its buffers are reused
+        off, full = self._window_cols(name)
+        launch(full[self.c0:self.c1])
+        return self._p2p_pending(name, full, self.window.gather(off, self.c0, self.c1 - self.c0))
+
+    def _p2p_rows(self, name: str, launch, divisor: float = 0.0) -> Pending:
+        prev = self._inflight.pop(name, None)
+        if prev is not None:
+            prev.wait()  # peers read my partial until that exchange has ended
+        (poff, partial), (roff, result) = self._window_rows(name)
+        launch(partial)
+        return self._p2p_pending(name, result, self.window.reduce(poff, roff, self.nrow, divisor))
+
+    def _buf(self, name: str, n: int) -> torch.Tensor:
+        t = self._bufs.get(name)
+        if t is None:
+            t = self._bufs[name] = torch.empty(n, dtype=torch.float64, device=self.device)
+        return t
+
+    @staticmethod
+    def _done(p: Pending, async_op: bool):
+        return p if async_op else p.wait()
 
     # ---- column-indexed: disjoint slices + all-gather --------------------------------------------------
-    def _gather_columns(self) -> torch.Tensor:
-        mine = self._col_full[self.c0:self.c1]
+    def _gather_columns(self, full: torch.Tensor) -> Pending:
         if self.world == 1:
-            return self._col_full
+            return Pending(full)
         if self._even:
-            dist.all_gather_into_tensor(self._col_full, mine.clone(), group=self.group)
-        else:
-            parts = [self._col_full[self.bounds[k]:self.bounds[k + 1]] for k in range(self.world)]
-            # uneven counts: one broadcast per owner (grouped by the backend)
-            for k in range(self.world):
-                if parts[k].numel():
-                    dist.broadcast(parts[k], src=dist.get_global_rank(self.group, k) if self.group else k,
-                                   group=self.group)
-        return self._col_full
+            mine = full[self.c0:self.c1].clone()  # kept alive by the Pending until the gather has run
+            w = dist.all_gather_into_tensor(full, mine, group=self.group, async_op=True)
+            p = Pending(full, [w])
+            p._keep = mine
+            return p
+        works = []
+        # uneven counts: one broadcast per owner (grouped by the backend)
+        for k in range(self.world):
+            part = full[self.bounds[k]:self.bounds[k + 1]]
+            if part.numel():
+                works.append(dist.broadcast(part, src=dist.get_global_rank(self.group, k) if self.group else k,
+                                            group=self.group, async_op=True))
+        return Pending(full, works)
 
-    def colSums(self) -> torch.Tensor:
-        self.local.col_sums(self._col_full[self.c0:self.c1], 0.0)
-        return self._gather_columns()
+    def colSums(self, async_op: bool = False):
+        if self.window is not None:
+            return self._done(self._p2p_cols("colSums", lambda out: self.local.col_sums(out, 0.0)), async_op)
+        full = self._buf("colSums", self.ncol)
+        self.local.col_sums(full[self.c0:self.c1], 0.0)
+        return self._done(self._gather_columns(full), async_op)
 
-    def colMeans(self) -> torch.Tensor:
-        self.local.col_sums(self._col_full[self.c0:self.c1], float(self.nrow))  # nrow is global already
-        return self._gather_columns()
+    def colMeans(self, async_op: bool = False):
+        if self.window is not None:
+            return self._done(self._p2p_cols("colMeans", lambda out: self.local.col_sums(out, float(self.nrow))), async_op)
+        full = self._buf("colMeans", self.ncol)
+        self.local.col_sums(full[self.c0:self.c1], float(self.nrow))  # nrow is global already
+        return self._done(self._gather_columns(full), async_op)
 
-    def spmv_t(self, v: torch.Tensor) -> torch.Tensor:
+    def spmv_t(self, v: torch.Tensor, async_op: bool = False):
         """A^T v: v[nrow] replicated on every rank."""
-        self.local.spmv_t(v, self._col_full[self.c0:self.c1])
-        return self._gather_columns()
+        if self.window is not None:
+            return self._done(self._p2p_cols("spmv_t", lambda out: self.local.spmv_t(v, out)), async_op)
+        full = self._buf("spmv_t", self.ncol)
+        self.local.spmv_t(v, full[self.c0:self.c1])
+        return self._done(self._gather_columns(full), async_op)
 
     # ---- row-indexed: full-length partials + all-reduce ----------------------------------------------------
-    def _reduce_rows(self) -> torch.Tensor:
+    def _reduce_rows(self, full: torch.Tensor, finish=None) -> Pending:
+        works = []
         if self.world > 1:
-            dist.all_reduce(self._row_full, op=dist.ReduceOp.SUM, group=self.group)
-        return self._row_full
+            works.append(dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        return Pending(full, works, finish)
 
-    def rowSums(self) -> torch.Tensor:
-        self.local.row_sums(self._row_full)
-        return self._reduce_rows()
+    def rowSums(self, async_op: bool = False):
+        if self.window is not None:
+            return self._done(self._p2p_rows("rowSums", self.local.row_sums), async_op)
+        full = self._buf("rowSums", self.nrow)
+        self.local.row_sums(full)
+        return self._done(self._reduce_rows(full), async_op)
 
-    def rowMeans(self) -> torch.Tensor:
-        self.local.row_sums(self._row_full)
-        out = self._reduce_rows()
-        self.local.div(out, float(self.ncol))  # GLOBAL ncol (RcppSparse.h:154 divides by Dim[1])
-        return out
+    def rowMeans(self, async_op: bool = False):
+        if self.window is not None:  # the division by the GLOBAL ncol rides in the reduction kernel
+            return self._done(self._p2p_rows("rowMeans", self.local.row_sums, float(self.ncol)), async_op)
+        full = self._buf("rowMeans", self.nrow)
+        self.local.row_sums(full)
+        # GLOBAL ncol, after the reduce (RcppSparse.h:154 divides the finished sums by Dim[1])
+        return self._done(self._reduce_rows(full, lambda: self.local.div(full, float(self.ncol))), async_op)
 
-    def spmv(self, v: torch.Tensor) -> torch.Tensor:
+    def spmv(self, v: torch.Tensor, async_op: bool = False):
         """A v: v[ncol] replicated; each rank uses only its own slice."""
-        self.local.spmv(v[self.c0:self.c1], self._row_full)
-        return self._reduce_rows()
+        if self.window is not None:
+            return self._done(self._p2p_rows("spmv", lambda out: self.local.spmv(v[self.c0:self.c1], out)), async_op)
+        full = self._buf("spmv", self.nrow)
+        self.local.spmv(v[self.c0:self.c1], full)
+        return self._done(self._reduce_rows(full), async_op)
 
     # ---- transpose: local transposes + ONE exchange step (all-to-all-v) --------------------------------------
     def transpose(self):

@@ -75,6 +75,16 @@ def _worker(rank, world, port, balanced, q):
         }
         for op, (got, want, v) in checks.items():
             oracle.assert_within(op, got, want, *args, v=v)
+        # the same six sweeps launched back to back with their collectives left in flight (what bench.py does
+        # so that op k's collective overlaps op k+1's sweep), waited afterwards in a different order
+        pend = {"colSums": S.colSums(async_op=True), "rowSums": S.rowSums(async_op=True),
+                "colMeans": S.colMeans(async_op=True), "rowMeans": S.rowMeans(async_op=True),
+                "spmv": S.spmv(v_c, async_op=True), "spmv_t": S.spmv_t(v_r, async_op=True)}
+        for op in ("rowMeans", "spmv_t", "colSums", "spmv", "colMeans", "rowSums"):
+            got = pend[op].wait().numpy()
+            oracle.assert_within(op, got, checks[op][1], *args, v=checks[op][2])
+            assert pend[op].wait() is pend[op].tensor  # a second wait is a no-op (no second division)
+            oracle.assert_within(op, pend[op].tensor.numpy(), checks[op][1], *args, v=checks[op][2])
         # sharded transpose: my row block of A^T must equal the same rows of the full transpose, bit for bit
         rb, tp_own, tcols, tvals = S.transpose()
         fi, fp, fx = full.transpose(*args)
