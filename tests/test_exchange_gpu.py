@@ -45,7 +45,8 @@ def test_window_world1_reduce_gather_and_bounds():
         main.wait_event(W.reduce(poff, roff, n, 0.0))
         assert torch.equal(res, part)
         main.wait_event(W.reduce(poff, roff, n, 7.0))
-        assert torch.equal(res, part / 7.0)  # IEEE division, as the mean's sums / Dim
+        # IEEE division, as the mean's sums / Dim (numpy divides; torch multiplies by the scalar's reciprocal on CUDA)
+        assert np.array_equal(res.cpu().numpy(), part.cpu().numpy() / 7.0)
         col.fill_(3.0)
         main.wait_event(W.gather(coff, 10, n - 10))  # world 1: nothing to push, nothing to wait for
         main.wait_event(W.barrier())
