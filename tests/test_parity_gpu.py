@@ -19,6 +19,12 @@ def bits(a):
     return np.ascontiguousarray(a, np.float64).view(np.uint64)
 
 
+def zlib_seed(name):
+    import zlib
+
+    return zlib.crc32(name.encode())
+
+
 @pytest.fixture(scope="module")
 def checker():
     return oracle.best()  # the compiled reference when it travelled to this box, else the C port
@@ -129,6 +135,57 @@ def test_synth_transpose_bit_exact(synth_case, checker):
     assert np.array_equal(T.i, ti), name
     assert np.array_equal(bits(T.x), bits(tx)), name
     A.release()
+
+
+def _columns_of_lengths(lengths, nrow, seed):
+    rng = np.random.default_rng(seed)
+    p = np.zeros(len(lengths) + 1, np.int64)
+    p[1:] = np.cumsum(lengths)
+    i = np.empty(int(p[-1]), np.int32)
+    for c, n in enumerate(lengths):
+        if n:
+            start = int(rng.integers(0, nrow - n + 1))
+            gaps = np.sort(rng.choice(nrow - start, n, replace=False)) if n < (nrow - start) // 2 else np.arange(n)
+            i[p[c]:p[c + 1]] = start + gaps
+    x = rng.standard_normal(int(p[-1])) * np.exp(rng.uniform(-3, 3, int(p[-1])))
+    return i, p.astype(np.int32), x
+
+
+# column-length regimes of the sweep kernel (sweep.cu): tiles of 2816 (sums) / 1792 (A^T v) items take the
+# per-thread walk with 0-1 column ends, a warp per column with 2-7, 8 lanes per column with 8-512, the walk again
+# beyond; every boundary, constant and mixed, including empty columns between long ones
+LENGTH_REGIMES = {
+    "const_0_1_2": [0] * 700 + [1] * 3000 + [2] * 3000,
+    "const_3": [3] * 9000, "const_4": [4] * 7000, "const_5": [5] * 6000, "const_6": [6] * 5000,
+    "const_10": [10] * 4000, "const_44": [44] * 900, "const_100": [100] * 500,
+    "const_223_224_225": [223] * 90 + [224] * 90 + [225] * 90,
+    "const_351_352_353": [351] * 60 + [352] * 60 + [353] * 60,
+    "const_402_403": [402] * 60 + [403] * 60,
+    "const_938_939_940": [938] * 30 + [939] * 30 + [940] * 30,
+    "const_1407_1408": [1407] * 25 + [1408] * 25,
+    "const_2815_2816_2817": [2815] * 12 + [2816] * 12 + [2817] * 12,
+    "long_then_dust": [5600] * 3 + [1] * 4000 + [5600] * 2 + [0] * 3000 + [7] * 2000 + [5000],
+    "sawtooth": [n for k in range(120) for n in (2900, 0, 3, 350, 9, 1, 1500, 0, 0, 60)],
+}
+
+
+@pytest.mark.parametrize("regime", sorted(LENGTH_REGIMES))
+def test_sweep_column_length_regimes(regime, checker):
+    lengths = LENGTH_REGIMES[regime]
+    nrow = 6000
+    i, p, x = _columns_of_lengths(lengths, nrow, zlib_seed(regime))
+    ncol = len(lengths)
+    args = (i, p, x, nrow, ncol)
+    v_row = synth.dense_vector(5, nrow)
+    with DeviceMatrix.from_host(*args) as D:
+        oracle.assert_within("colSums", D.col_sums(), checker.colSums(*args), *args, tol=TOL)
+        oracle.assert_within("colMeans", D.col_means(), checker.colMeans(*args), *args, tol=TOL)
+        oracle.assert_within("spmv_t", D.spmv_t(v_row), checker.spmv_t(*args, v_row), *args, v=v_row, tol=TOL)
+        a, b = D.col_sums(), D.col_sums()
+        assert np.array_equal(bits(a), bits(b)), "column sums must be bit-stable run to run"
+        D.row_companion(1)  # the row-ordered copy is swept by the same kernel, with its own length regime
+        oracle.assert_within("rowSums", D.row_sums(), checker.rowSums(*args), *args, tol=TOL)
+        oracle.assert_within("rowMeans", D.row_means(), checker.rowMeans(*args), *args, tol=TOL)
 
 
 @pytest.mark.parametrize("row_plan", ["0", "1"])
