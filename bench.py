@@ -327,7 +327,7 @@ def run_b200(args, ops):
                 t0 = time.perf_counter()
                 D.row_companion(1)  # what the 9th call would do on its own; explicit so that it is timed, and so that
                 torch.cuda.synchronize()  # it precedes the warm-up whatever --warmup is
-                row_companion.update(built=True, build_ms=(time.perf_counter() - t0) * 1e3, extra_hbm_bytes=8 * nnz + 4 * (D.nrow + 1))
+                row_companion.update(built=True, build_ms=(time.perf_counter() - t0) * 1e3, extra_hbm_bytes=12 * nnz + 4 * (D.nrow + 1))
             except Exception as e:
                 row_companion["error"] = f"{type(e).__name__}: {e}"
         del out_r

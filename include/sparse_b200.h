@@ -117,14 +117,15 @@ int sb200_vec_div_dev(sb200_matrix* m, double* d, int64_t n, double divisor);
  * Decided once per handle from the shape; SB200_ROW_PLAN=0/1 overrides. */
 int sb200_matrix_row_path(sb200_matrix* m, int* banded);
 
-/* Row-major companion of a RESIDENT mirror.  rowSums / rowMeans scatter by row index when they run on the
- * CSC arrays (the reference's loop, RcppSparse.h:137-143, 153-160); a mirror that is asked for them more
+/* Row-major companion of a RESIDENT mirror.  rowSums / rowMeans / A v scatter by row index when they run on
+ * the CSC arrays (the reference's loop, RcppSparse.h:137-143, 153-160); a mirror that is asked for them more
  * than SB200_ROW_COMPANION_AFTER times (default 8; 0 = never) and owns its arrays (created from host
  * buffers, generated or transposed here — not adopted device arrays, whose values the caller may change
- * behind the mirror) keeps a row-ordered copy of x with a row pointer (one device transpose, + 8 B per entry
- * of HBM) and serves them as streaming segmented sums from then on; sb200_matrix_row_path reports 2.
- * sb200_matrix_refresh_values drops the copy.  action: 1 = build now (also for adopted arrays: the caller
- * promises to call this again, or refresh, after changing values), 0 = drop, -1 = drop and never build. */
+ * behind the mirror) keeps a row-ordered copy of itself (one device transpose, + 12 B per entry of HBM) and
+ * serves the row sums as streaming segmented sums and A v as a gather sweep from then on;
+ * sb200_matrix_row_path reports 2.  sb200_matrix_refresh_values drops the copy.  action: 1 = build now (also
+ * for adopted arrays: the caller promises to call this again, or refresh, after changing values), 0 = drop,
+ * -1 = drop and never build. */
 int sb200_matrix_row_companion(sb200_matrix* m, int action);
 
 /* ---- cross-GPU exchange for column-sharded matrices (one process per GPU, GPUs of one node) ---------

@@ -1098,6 +1098,224 @@ int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out) {
   return SB200_OK;
 }
 
+// ================================================================================================
+// A^T v with the operand in shared memory (banded gather)
+// ================================================================================================
+// sweep_kernel<SPMV_T> gathers v[i[k]] from L2, one 8-byte request per entry: its ceiling is the L2 request rate
+// (245 G gathers/s measured = 0.41 ms per 1e8 entries), a third of what HBM would allow.  Here a CTA (row band,
+// column split) keeps v's slice of its band in shared memory and walks the band's run of every column of its
+// split: the gathers become LDS, HBM sees i and x once (plus band pointers) and 8 bytes per (column, band) of
+// partial results (REDs at L2, or plain stores when one band covers all rows).
+//   A warp takes 32 columns (one run descriptor per lane) and sums them G lanes per column, 32/G columns at a
+//   time, G picked per 32 columns from their mean run length (2, 8 or 32): the lanes of a group stride over
+//   the run (so a load instruction covers 32/G contiguous pieces), fold with shuffles, and the group's first
+//   lane stores.  Two rounds of loads are in flight per warp.  Runs much longer than their group are summed by
+//   the whole warp first.  No shared-memory atomics, no per-entry index lists.
+constexpr int GA_THREADS = 768;
+constexpr int GA_WARPS = GA_THREADS / 32;
+constexpr int GA_U = 4;      // loads per lane and round
+constexpr int GATHER_ROWS_CAP = (216 * 1024) / 8;  // 27648 rows of v per band
+
+struct GatherArgs {
+  BandView bv;
+  const double* v;
+  double* out;
+  int max_rows;
+};
+
+template <int G>
+__device__ __forceinline__ void gather_rounds(const BandView& bv, const double* __restrict__ vs, int32_t row0, int32_t s,
+                                              int32_t len, double extra, bool any, int lane, int64_t cg, int64_t c_hi,
+                                              double* __restrict__ out) {
+  constexpr int CPR = 32 / G;  // columns per round
+  const int sub = lane % G, grp = lane / G;
+#pragma unroll 1
+  for (int r = 0; r < G; r += 2) {  // two rounds per step: their loads are issued together
+    int32_t ks[2], ke[2];
+    double part[2] = {0.0, 0.0};
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int col = (r + w) * CPR + grp;
+      ks[w] = __shfl_sync(0xffffffffu, s, col & 31);
+      ke[w] = ks[w] + __shfl_sync(0xffffffffu, len, col & 31);
+      if (G == 1 || r + w >= G) ke[w] = ks[w];
+    }
+    int32_t k0[2] = {ks[0] + sub, ks[1] + sub};
+    while (__any_sync(0xffffffffu, k0[0] < ke[0] || k0[1] < ke[1])) {
+      int32_t rr[2][GA_U];
+      double xx[2][GA_U];
+#pragma unroll
+      for (int w = 0; w < 2; ++w)
+#pragma unroll
+        for (int t = 0; t < GA_U; ++t) {
+          const int32_t k = k0[w] + t * G;
+          rr[w][t] = -1;
+          xx[w][t] = 0.0;
+          if (k < ke[w]) {
+            rr[w][t] = ptx::ld_stream_s32(bv.i + k) - row0;
+            xx[w][t] = ptx::ld_stream_f64(bv.x + k);
+          }
+        }
+#pragma unroll
+      for (int w = 0; w < 2; ++w)
+#pragma unroll
+        for (int t = 0; t < GA_U; ++t)
+          if (rr[w][t] >= 0) part[w] = __dadd_rn(part[w], __dmul_rn(xx[w][t], vs[rr[w][t]]));  // idle lanes add nothing (no 0 * Inf)
+      k0[0] += G * GA_U;
+      k0[1] += G * GA_U;
+    }
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+#pragma unroll
+      for (int off = G / 2; off > 0; off >>= 1) part[w] = __dadd_rn(part[w], __shfl_xor_sync(0xffffffffu, part[w], off));
+      const int col = ((r + w) * CPR + grp) & 31;
+      const double total = __dadd_rn(part[w], __shfl_sync(0xffffffffu, extra, col));  // + the run the whole warp summed
+      const bool some = __shfl_sync(0xffffffffu, any ? 1 : 0, col) != 0;
+      const int64_t c = cg + (r + w) * CPR + grp;
+      if (sub == 0 && r + w < G && c < c_hi) {
+        if (bv.nb == 1)
+          out[c] = total;  // one band holds every row: the only contribution to this column (0 for an empty one)
+        else if (some)
+          ptx::red_add_f64(out + c, total);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GA_THREADS, 1) band_gather_kernel(const GatherArgs a) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const BandView& bv = a.bv;
+  double* vs = reinterpret_cast<double*>(gsm);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int units = bv.nb * bv.S;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int h = u / bv.nb, b = u % bv.nb;
+    const int32_t row0 = bv.rb[b];
+    const int32_t R = bv.rb[b + 1] - row0;
+    const int64_t c_lo = bv.cs[h], c_hi = bv.cs[h + 1];
+    __syncthreads();  // the previous unit's readers are done with vs
+    for (int r = tid; r < R; r += GA_THREADS) vs[r] = __ldg(a.v + row0 + r);
+    __syncthreads();
+    // descriptors one group ahead
+    int32_t ns = 0, ne = 0;
+    {
+      const int64_t c = c_lo + warp * 32 + lane;
+      if (c < c_hi && R > 0) {
+        ns = band_start(bv, b, c);
+        ne = band_start(bv, b + 1, c);
+      }
+    }
+    for (int64_t cg = c_lo + warp * 32; cg < c_hi; cg += GA_WARPS * 32) {
+      const int64_t c = cg + lane;
+      const int32_t s = ns;
+      int32_t len = ne - ns;
+      ns = ne = 0;
+      {
+        const int64_t cn = c + GA_WARPS * 32;
+        if (cn < c_hi && R > 0) {
+          ns = band_start(bv, b, cn);
+          ne = band_start(bv, b + 1, cn);
+        }
+      }
+      int32_t total = len;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+      if (total == 0) {
+        if (bv.nb == 1 && c < c_hi) a.out[c] = 0.0;
+        continue;
+      }
+      const bool any = len > 0;
+      const int mean = total >> 5;
+      const int32_t long_len = mean <= 6 ? 64 : (mean <= 48 ? 256 : 0x7fffffff);  // far beyond the group's reach
+      // ---- runs much longer than the rest: the whole warp on one run ----
+      double extra = 0.0;
+      unsigned longmask = __ballot_sync(0xffffffffu, len >= long_len);
+      while (longmask) {
+        const int src = __ffs(longmask) - 1;
+        longmask &= longmask - 1;
+        const int32_t rs = __shfl_sync(0xffffffffu, s, src);
+        const int32_t re = rs + __shfl_sync(0xffffffffu, len, src);
+        double part = 0.0;
+        for (int32_t k0 = rs; k0 < re; k0 += 32 * GA_U) {
+          int32_t rr[GA_U];
+          double xx[GA_U];
+#pragma unroll
+          for (int t = 0; t < GA_U; ++t) {
+            const int32_t k = k0 + t * 32 + lane;
+            rr[t] = -1;
+            xx[t] = 0.0;
+            if (k < re) {
+              rr[t] = ptx::ld_stream_s32(bv.i + k) - row0;
+              xx[t] = ptx::ld_stream_f64(bv.x + k);
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < GA_U; ++t)
+            if (rr[t] >= 0) part = __dadd_rn(part, __dmul_rn(xx[t], vs[rr[t]]));
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, off));
+        if (lane == src) {
+          extra = part;
+          len = 0;  // the rounds below skip it and add `extra` when they store the column
+        }
+      }
+      __syncwarp();
+      if (mean <= 6)
+        gather_rounds<2>(bv, vs, row0, s, len, extra, any, lane, cg, c_hi, a.out);
+      else if (mean <= 48)
+        gather_rounds<8>(bv, vs, row0, s, len, extra, any, lane, cg, c_hi, a.out);
+      else
+        gather_rounds<32>(bv, vs, row0, s, len, extra, any, lane, cg, c_hi, a.out);
+    }
+  }
+}
+
+// Opt-in (SB200_GATHER_PLAN=1), parity-tested, NOT the default: measured on B200 against sweep_kernel<SPMV_T>
+// (L2 gathers) it is 0.50 vs 0.495 ms at C2, 5.25 vs 5.03 ms at C3, 14.8 vs 9.5 ms at C4.  The gathers do become
+// LDS and DRAM traffic is the algorithmic 1.25 GB at C2, but the runs are fetched with register loads — at most
+// ~70 KB in flight per SM, and only in bursts — where the TMA-staged sweep keeps ~200 KB in flight; the kernel is
+// latency-bound (ncu: long_scoreboard 8.6 warps per issue, issue-active 33 %).  The next step is to stage the
+// runs with cp.async.bulk like the sweep does (profiles/r01/README.md).
+int decide_gather_path(sb200_matrix* m) {
+  if (m->gather_path >= 0) return SB200_OK;
+  int path = 0;
+  if (const char* e = getenv("SB200_GATHER_PLAN")) path = (e[0] != '0' && m->nnz > 0 && m->nrow > 0 && m->ncol > 0) ? 1 : 0;
+  m->gather_path = path;
+  return SB200_OK;
+}
+
+int launch_band_gather(sb200_matrix* m, const double* d_v, double* d_out) {
+  if (!m->plan_gather) {
+    int64_t nb = (static_cast<int64_t>(m->nrow) + static_cast<int64_t>(0.9 * GATHER_ROWS_CAP) - 1) /
+                 static_cast<int64_t>(0.9 * GATHER_ROWS_CAP);
+    if (nb < 1) nb = 1;
+    if (nb > 4096) return fail(SB200_E_UNSUPPORTED, "banded gather: too many row bands");
+    int S = static_cast<int>((2 * m->sm_count + nb - 1) / nb);  // two units per SM
+    if (S < 1) S = 1;
+    if (S > 1024) S = 1024;
+    SB_TRY(build_band_plan(m, GATHER_ROWS_CAP, static_cast<int>(nb), S, &m->plan_gather));
+  }
+  const BandPlan* bp = m->plan_gather;
+  GatherArgs a;
+  a.bv = make_view(m, bp);
+  a.v = d_v;
+  a.out = d_out;
+  a.max_rows = (bp->max_rows > 0 ? (bp->max_rows + 1) & ~1 : 2);
+  if (bp->nb > 1) SB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * static_cast<size_t>(m->ncol), m->stream));
+  const size_t smem = sizeof(double) * static_cast<size_t>(a.max_rows);
+  int ctas = static_cast<int>((220 * 1024) / (smem + 1024));
+  if (ctas > 2) ctas = 2;
+  if (ctas < 1) ctas = 1;
+  int grid = m->sm_count * ctas;
+  if (grid > bp->nb * bp->S) grid = bp->nb * bp->S;
+  SB_CUDA(cudaFuncSetAttribute(band_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  band_gather_kernel<<<grid, GA_THREADS, smem, m->stream>>>(a);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return SB200_OK;
+}
+
 // ---- transpose -------------------------------------------------------------------------------------------
 constexpr int TRANSPOSE_ROWS_CAP = 2432;  // 72 B of tables per row + 48 KB of flat lists: one CTA per SM at the cap, two when small
 
@@ -1190,6 +1408,10 @@ void free_matrix_plans(sb200_matrix* m, cudaStream_t s) {
   if (m->plan_scatter) {
     free_band_plan(m->plan_scatter, s);
     m->plan_scatter = nullptr;
+  }
+  if (m->plan_gather) {
+    free_band_plan(m->plan_gather, s);
+    m->plan_gather = nullptr;
   }
 }
 

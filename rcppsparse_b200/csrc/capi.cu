@@ -109,6 +109,7 @@ static int new_handle(int device, int32_t nrow, int32_t ncol, int64_t nnz, sb200
   memset(m, 0, sizeof(*m));
   m->magic = MATRIX_MAGIC;
   m->row_path = -1;
+  m->gather_path = -1;
   m->device = device;
   m->nrow = nrow;
   m->ncol = ncol;
@@ -180,9 +181,9 @@ void drop_row_companion(sb200_matrix* m) {
   m->row_sum_calls = 0;
 }
 
-// Transposed copy on the owner's stream, keeping only what a row sum reads (p over rows, x in row order, the
-// tile plan).  Costs one transpose and 8 B per entry of HBM; skipped when that would not
-// leave room to spare.  Failure is not the caller's problem: the scatter kernels keep serving the mirror.
+// Transposed copy on the owner's stream (row pointer, column ids and values in row order, tile plans).  Costs
+// one transpose and 12 B per entry of HBM; skipped when that would not leave room to spare.
+// Failure is not the caller's problem: the scatter kernels keep serving the mirror.
 int build_row_companion(sb200_matrix* m) {
   if (m->rows_state == 1) return SB200_OK;
   m->rows_state = -1;
@@ -203,11 +204,7 @@ int build_row_companion(sb200_matrix* m) {
     t->owns_stream = false;
     t->rows_state = -1;
     rc = transpose_device(m, t->d_p, t->d_i, t->d_x);
-    if (rc == SB200_OK) {
-      pool_free(t->d_i, m->stream);
-      t->d_i = nullptr;
-      rc = finish_matrix(t, SB200_NO_VALIDATE);
-    }
+    if (rc == SB200_OK) rc = finish_matrix(t, SB200_NO_VALIDATE);
   }
   if (rc != SB200_OK) {
     if (t) free_matrix(t);

@@ -84,12 +84,14 @@ struct sb200_matrix {
   // row-band plan for the row-indexed sweeps (bands.cu); structure-only, built on first use
   sb200::BandPlan* plan_scatter;
   int row_path;  // -1 undecided, 0 plan-free L2 atomics, 1 banded (decide_row_path)
-  // Row-major companion for rowSums / rowMeans on a resident mirror (capi.cu, build_row_companion): the
-  // transposed copy's p (over rows) and x (in row order); its i is released.  Built after
-  // `row_companion_after()` row-sum calls on a mirror that owns its arrays, dropped by refresh_values.
+  sb200::BandPlan* plan_gather;  // wider bands (v's slice in shared memory) for A^T v, built on first use
+  int gather_path;               // -1 undecided, 0 sweep_kernel<SPMV_T> (L2 gathers), 1 banded gather
+  // Row-major companion for rowSums / rowMeans / A v on a resident mirror (capi.cu, build_row_companion): the
+  // transposed copy.  Built after `row_companion_after()` row-indexed calls on a mirror that owns its arrays,
+  // dropped by refresh_values.
   sb200_matrix* rows;
   int rows_state;     // 0 not built, 1 built, -1 never (disabled, or the build failed once)
-  int row_sum_calls;  // row-sum calls served by the scatter kernels since the last (re)build decision
+  int row_sum_calls;  // row-indexed calls served by the scatter kernels since the last (re)build decision
 };
 
 namespace sb200 {
@@ -133,6 +135,8 @@ int exclusive_scan_u32(cudaStream_t s, const uint32_t* d_in, int32_t* d_out, int
 int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double* d_x_out);
 int ensure_scatter_plan(sb200_matrix* m);
 int decide_row_path(sb200_matrix* m);
+int decide_gather_path(sb200_matrix* m);
+int launch_band_gather(sb200_matrix* m, const double* d_v, double* d_out);
 int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out);  // d_v null = rowSums
 void free_matrix_plans(sb200_matrix* m, cudaStream_t s);
 int build_row_companion(sb200_matrix* m);  // capi.cu; non-fatal: leaves rows_state = -1 when it cannot be built

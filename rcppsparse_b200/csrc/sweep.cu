@@ -611,17 +611,29 @@ int launch_vec_div(cudaStream_t s, double* d, int64_t n, double divisor) {
 }
 
 int launch_sweep(sb200_matrix* m, SweepMode mode, const double* d_v, double divisor, double* d_out) {
-  if (mode == SWEEP_ROWSUM && m->nnz > 0 && m->nrow > 0) {
-    // A mirror whose row sums keep being asked for gets a row-major copy of its values: from then on a row
-    // sum is the same streaming segmented sweep as a column sum (8 B per entry, no atomics) instead of a
-    // scatter.  Same arithmetic every call — only the layout is kept, like the band plan.
+  if ((mode == SWEEP_ROWSUM || mode == SWEEP_SPMV) && m->nnz > 0 && m->nrow > 0) {
+    // A mirror whose row-indexed sweeps keep being asked for gets a row-major copy of itself: from then on a
+    // row sum is the same streaming segmented sweep as a column sum (8 B per entry, no atomics) and A v is the
+    // gather sweep of the copy (A v = (A^T)^T v) instead of a scatter.  Same arithmetic every call — only the
+    // layout is kept, like the band plan.
     if (m->rows_state == 0 && m->owns_arrays) {
       const int after = row_companion_after();
       if (after > 0 && ++m->row_sum_calls > after) build_row_companion(m);
     }
     if (m->rows_state == 1) {
       m->rows->stream = m->stream;
-      return launch_sweep(m->rows, SWEEP_COLSUM, nullptr, divisor, d_out);
+      if (mode == SWEEP_ROWSUM) return launch_sweep(m->rows, SWEEP_COLSUM, nullptr, divisor, d_out);
+      return launch_sweep(m->rows, SWEEP_SPMV_T, d_v, 0.0, d_out);
+    }
+  }
+  if (mode == SWEEP_SPMV_T && m->nnz > 0) {
+    SB_TRY(decide_gather_path(m));
+    if (m->gather_path == 1) {
+      const int rc = launch_band_gather(m, d_v, d_out);
+      if (rc == SB200_OK) return SB200_OK;
+      if (rc != SB200_E_UNSUPPORTED && rc != SB200_E_NOMEM) return rc;
+      cudaGetLastError();  // no plan for this shape: the L2-gather sweep serves every shape
+      m->gather_path = 0;
     }
   }
   if (mode == SWEEP_ROWSUM || mode == SWEEP_SPMV) SB_TRY(decide_row_path(m));

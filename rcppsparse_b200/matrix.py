@@ -126,7 +126,7 @@ class DeviceMatrix:
 
     def row_path(self) -> str:
         """'banded' or 'l2-atomics': which kernel serves rowSums / rowMeans / A v for this matrix;
-        'row-companion' once rowSums / rowMeans run on the row-ordered copy (A v keeps the scatter kernel)."""
+        'row-companion' once rowSums / rowMeans / A v run on the row-ordered copy."""
         b = C.c_int()
         check(_lib.lib().sb200_matrix_row_path(self._h, C.byref(b)))
         return ("l2-atomics", "banded", "row-companion")[b.value]

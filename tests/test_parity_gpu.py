@@ -188,6 +188,20 @@ def test_sweep_column_length_regimes(regime, checker):
         oracle.assert_within("rowMeans", D.row_means(), checker.rowMeans(*args), *args, tol=TOL)
 
 
+@pytest.mark.parametrize("case", ["C1_full", "C2_scaled", "C3_scaled", "C4_scaled", "many_tiny_columns", "few_huge_columns"])
+def test_banded_gather_opt_in_parity(case, checker, monkeypatch):
+    """A^T v with v's band slice in shared memory (bands.cu, band_gather_kernel; opt-in, SB200_GATHER_PLAN=1):
+    lane groups of 2 / 8 / 32 per column and the whole-warp path for outlier runs, against the reference."""
+    monkeypatch.setenv("SB200_GATHER_PLAN", "1")
+    spec = SYNTH_CASES[case]()
+    i, p, x = synth.generate_host(spec)
+    args = (i, p, x, spec.nrow, spec.ncol)
+    v_row = synth.dense_vector(spec.seed + 7, spec.nrow)
+    with DeviceMatrix.from_host(*args) as D:
+        for _ in range(2):
+            oracle.assert_within("spmv_t", D.spmv_t(v_row), checker.spmv_t(*args, v_row), *args, v=v_row, tol=TOL)
+
+
 @pytest.mark.parametrize("row_plan", ["0", "1"])
 @pytest.mark.parametrize("case", ["C2_scaled", "C3_scaled", "many_tiny_columns"])
 def test_row_indexed_ops_on_both_paths(row_plan, case, monkeypatch, checker):
@@ -355,7 +369,7 @@ def test_row_companion_parity_and_lifecycle(name):
         oracle.assert_within("rowSums", D.row_sums(), chk.rowSums(*args), *args, tol=TOL)
         oracle.assert_within("rowMeans", D.row_means(), chk.rowMeans(*args), *args, tol=TOL)
         v = synth.dense_vector(3, spec.ncol)
-        oracle.assert_within("spmv", D.spmv(v), chk.spmv(*args, v), *args, v=v, tol=TOL)  # unaffected
+        oracle.assert_within("spmv", D.spmv(v), chk.spmv(*args, v), *args, v=v, tol=TOL)  # A v = the gather sweep of the copy
         x2 = x * -0.5 + 1.0
         D.refresh_values(x2)
         assert D.row_path() == before
