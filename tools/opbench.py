@@ -22,7 +22,8 @@ ABI = {"colSums": "col_sums", "rowSums": "row_sums", "colMeans": "col_means", "r
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--workload", default="C2", help="C1..C4, or uniform:NROW:NCOL:DENSITY:SEED / powerlaw:NROW:NCOL:MEAN:SEED")
+    ap.add_argument("--flush-l2", action="store_true", help="write a 512 MB buffer between repetitions (inputs smaller than L2)")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--ops", default="colSums,rowSums,colMeans,rowMeans,spmv,spmv_t,transpose")
     ap.add_argument("--reps", type=int, default=20)
@@ -38,7 +39,17 @@ def main():
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         peak = 6650.0
-    spec = synth.config(a.workload, a.scale)
+    if ":" in a.workload:
+        kind, nrow, ncol, par, seed = a.workload.split(":")
+        if kind == "uniform":
+            spec = synth.uniform_spec(int(nrow), int(ncol), float(par), int(seed), name=a.workload)
+        elif kind == "powerlaw":
+            spec = synth.powerlaw_spec(int(nrow), int(ncol), float(par), int(seed), name=a.workload)
+        else:
+            raise SystemExit(f"unknown workload kind {kind}")
+    else:
+        spec = synth.config(a.workload, a.scale)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float64, device="cuda") if a.flush_l2 else None
     D = DeviceMatrix.synth(spec)
     D.set_stream(torch.cuda.current_stream().cuda_stream)
     if a.companion:
@@ -75,6 +86,8 @@ def main():
         torch.cuda.synchronize()
         ms = []
         for _ in range(a.reps):
+            if flush is not None:
+                flush.fill_(0.0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             run(op)
