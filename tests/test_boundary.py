@@ -91,3 +91,29 @@ def test_missing_library_raises(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(ImportError):
         _lib.lib()
+
+
+# ---- the R package around the drop-in: R is not installed here, so what can be checked is that
+# every layer names the same entry points -------------------------------------------------------------------------
+def test_r_package_entry_points_consistent():
+    pkg = os.path.join(ROOT, "r-package")
+    exports_cpp = open(os.path.join(pkg, "src", "exports.cpp")).read()
+    rcpp_exports = open(os.path.join(pkg, "src", "RcppExports.cpp")).read()
+    r_code = "".join(open(os.path.join(pkg, "R", f)).read() for f in sorted(os.listdir(os.path.join(pkg, "R"))))
+    namespace = open(os.path.join(pkg, "NAMESPACE")).read()
+    # functions tagged for export in C++ (name and arity)
+    tagged = {m.group(1): len([a for a in m.group(2).split(",") if a.strip()])
+              for m in re.finditer(r"//\[\[Rcpp::export\]\]\s*\n[\w:<>&\s]+?\b(\w+)\(([^)]*)\)", exports_cpp)}
+    assert "columnSums" in tagged and tagged["columnSums"] == 1  # the reference's exported function, same arity
+    # the registration table: one entry per tagged function, arity registered (reference src/RcppExports.cpp:26-30)
+    table = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"_RcppSparse_(\w+)", \(DL_FUNC\) &_RcppSparse_\1, (\d+)\}', rcpp_exports)}
+    assert table == tagged
+    assert "R_useDynamicSymbols(dll, FALSE)" in rcpp_exports
+    # every .Call in the R code hits a registered entry, and every registered entry is reachable from R
+    called = set(re.findall(r"\.Call\(`_RcppSparse_(\w+)`", r_code))
+    assert called == set(table)
+    # NAMESPACE exports exist as R functions
+    exported = set(sum((re.split(r"\s*,\s*", m) for m in re.findall(r"export\(([^)]*)\)", namespace)), []))
+    defined = set(re.findall(r"^(\w+)\s*<-\s*function", r_code, flags=re.M))
+    assert exported and exported <= defined, exported - defined
+    assert "useDynLib(RcppSparse, .registration = TRUE)" in namespace

@@ -100,3 +100,21 @@ def test_dropin_corrupt_index_is_an_exception(shim):
     out = np.empty(3)
     assert shim.dropin_reduce(2, i, p, x, 3, 1, 2, out) == 1  # invalid_argument; reference: index_out_of_bounds
     assert b"row index outside" in shim.dropin_last_error()
+
+
+def test_r_package_glue_type_checks():
+    """r-package/src/exports.cpp (the exported R entry points and the persistent external-pointer handle) against
+    the drop-in header; R and Rcpp are absent, so the test-only stand-in provides the Rcpp names."""
+    import os
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(root, "include"),
+                        "-I", os.path.join(root, "oracle", "stub"),
+                        "-include", os.path.join(root, "tests", "dropin", "rcpp_xptr_stub.h"),
+                        os.path.join(root, "r-package", "src", "exports.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
