@@ -7,13 +7,14 @@
 //   constructors (4 vectors / S4 / default)                reference :33-42
 //   rows cols nrow ncol n_nonzero nonzeros innerIndexPtr outerIndexPtr InnerNNZs   :44-51, :357-359
 //   colSums rowSums colMeans rowMeans                      reference :131-156  -> sb200_col_sums ... sb200_row_means
+//   crossprod                                              reference :158-194  -> sb200_crossprod
 //   transpose (and the vignette's t)                       reference :375-385  -> sb200_transpose
 //   wrap, clone, at, operator(), operator[]                reference :387-394, :54-73 (host side, unchanged semantics)
 //   InnerIterator                                          reference :218-233 (host side, unchanged)
 //   Rcpp::traits::Exporter<RcppSparse::Matrix>             reference :398-423
 // Additions: spmv(v) = A v and spmv_t(v) = A^T v (the reference only has the iterator idiom),
 // refresh() after mutating x in place, release() to drop the device mirror early.
-// Not provided here (off the hot path): crossprod, the range/row iterators,
+// Not provided here (off the hot path): the range/row iterators,
 // dense block extraction, isAppxSymmetric, InnerIndices.
 //
 // Include order: like the reference, this header must come BEFORE <Rcpp.h> in a translation unit
@@ -147,6 +148,13 @@ public:
     Rcpp::NumericVector means(Dim[0]);
     b200::check(sb200_row_means(mirror(), means.begin()));
     return means;
+  }
+
+  // dense A^T A (reference :158-194): ncol x ncol, exactly symmetric -> sb200_crossprod
+  Rcpp::NumericMatrix crossprod() {
+    Rcpp::NumericMatrix res(Dim[1], Dim[1]);
+    b200::check(sb200_crossprod(mirror(), res.begin()));
+    return res;
   }
 
   // y = A v (v has ncol entries) and y = A^T v (v has nrow entries)

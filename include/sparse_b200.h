@@ -112,6 +112,13 @@ int sb200_transpose_dev(sb200_matrix* m, sb200_matrix** out);
 /* d[k] /= divisor for k < n, on the handle's stream (mean scaling after a cross-rank reduce). */
 int sb200_vec_div_dev(sb200_matrix* m, double* d, int64_t n, double divisor);
 
+/* Dense A^T A (reference Matrix::crossprod(), RcppSparse.h:158-194): ncol x ncol doubles, column-major, exactly
+ * symmetric.  Computed as the sum over rows of (row)^T (row) on the row-ordered copy of the mirror (built, and
+ * kept, for mirrors that own their arrays; temporary otherwise).  Entries agree with the reference within
+ * 1e-12 * sum |a_ri a_rj| (the additions inside an entry are not in the reference's ascending-row order). */
+int sb200_crossprod(sb200_matrix* m, double* out /* ncol*ncol, host */);
+int sb200_crossprod_dev(sb200_matrix* m, double* d_out /* ncol*ncol, device */);
+
 /* Which kernel serves the row-indexed sweeps of this matrix: *banded = 1 shared-memory row bands
  * (a band plan is built on first use and cached with the mirror), 0 = plan-free L2 atomics.
  * Decided once per handle from the shape; SB200_ROW_PLAN=0/1 overrides. */

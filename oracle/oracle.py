@@ -57,6 +57,8 @@ class Port:
         L.oport_spmv.argtypes = [_i32p, _i32p, _f64p, C.c_int, C.c_int, _f64p, _f64p]
         L.oport_spmv_t.argtypes = [_i32p, _i32p, _f64p, C.c_int, _f64p, _f64p]
         L.oport_abs_colSums.argtypes = [_i32p, _f64p, C.c_int, _f64p]
+        L.oport_crossprod.argtypes = [_i32p, _i32p, _f64p, C.c_int, _f64p]
+        L.oport_crossprod.restype = None
         for f in ("oport_colSums", "oport_columnSums", "oport_rowSums", "oport_colMeans", "oport_rowMeans",
                   "oport_spmv", "oport_spmv_t", "oport_abs_colSums"):
             getattr(L, f).restype = None
@@ -66,6 +68,13 @@ class Port:
         i, p, x = _prep(i, p, x)
         out = np.empty(ncol, np.float64)
         self.L.oport_colSums(p, x, ncol, out)
+        return out
+
+    def crossprod(self, i, p, x, nrow, ncol):
+        """Dense A^T A as an (ncol, ncol) array (symmetric, so memory order does not matter)."""
+        i, p, x = _prep(i, p, x)
+        out = np.empty((ncol, ncol), np.float64)
+        self.L.oport_crossprod(i, p, x, ncol, out.reshape(-1))
         return out
 
     def columnSums(self, i, p, x, nrow, ncol):
@@ -146,6 +155,9 @@ class Ref:
         L.oref_spmv_t.argtypes = common + [_f64p, _f64p]
         L.oref_spmv_t.restype = C.c_int
         L.oref_last_error.restype = C.c_char_p
+        if hasattr(L, "oref_crossprod"):
+            L.oref_crossprod.argtypes = common + [_f64p]
+            L.oref_crossprod.restype = C.c_int
         self.L = L
 
     def _check(self, rc):
@@ -163,6 +175,13 @@ class Ref:
 
     def colSums(self, i, p, x, nrow, ncol):
         return self._vec(self.L.oref_colSums, i, p, x, nrow, ncol, ncol)
+
+    def crossprod(self, i, p, x, nrow, ncol):
+        i, p, x = _prep(i, p, x)
+        ipad = np.concatenate([i, np.array([nrow], np.int32)])  # the reference reads i[] one past a column's end
+        out = np.empty((ncol, ncol), np.float64)
+        self._check(self.L.oref_crossprod(ipad, p, x, nrow, ncol, x.shape[0], out.reshape(-1)))
+        return out
 
     def rowSums(self, i, p, x, nrow, ncol):
         return self._vec(self.L.oref_rowSums, i, p, x, nrow, ncol, nrow)
@@ -225,6 +244,10 @@ def abs_feed(op: str, i, p, x, nrow, ncol, v=None) -> np.ndarray:
         return np.bincount(i, weights=ax * np.abs(np.asarray(v)[col_of]), minlength=nrow)
     if op == "spmv_t":
         return np.bincount(col_of, weights=ax * np.abs(np.asarray(v)[i]), minlength=ncol)
+    if op == "crossprod":  # |A|^T |A|, dense (small n only)
+        dense = np.zeros((nrow, ncol))
+        dense[i, col_of] = ax
+        return dense.T @ dense
     raise KeyError(op)
 
 

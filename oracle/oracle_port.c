@@ -47,6 +47,34 @@ void oport_rowSums(const int* i, const int* p, const double* x, int nrow, int nc
     for (int j = p[col]; j < p[col + 1]; ++j) sums[i[j]] += x[j];
 }
 
+/* RcppSparse.h:158-194 — dense A^T A (n x n, column-major): for every pair of columns a two-pointer merge of
+ * their sorted row lists, products added in ascending row order; the lower triangle is a copy of the upper.
+ * Same arithmetic as the reference, with the bound tested BEFORE the index is read (the reference reads i[]
+ * one past the column end, :178-184; harmless there, undefined here). */
+void oport_crossprod(const int* i, const int* p, const double* x, int ncol, double* res) {
+  memset(res, 0, sizeof(double) * (size_t)ncol * (size_t)ncol);
+  for (int c1 = 0; c1 < ncol; ++c1) {
+    for (int c2 = c1; c2 < ncol; ++c2) {
+      double acc = 0.0;
+      int a = p[c1], b = p[c2];
+      const int ae = p[c1 + 1], be = p[c2 + 1];
+      while (a < ae && b < be) {
+        if (i[a] == i[b]) {
+          acc += x[a] * x[b];
+          ++a;
+          ++b;
+        } else if (i[a] < i[b]) {
+          ++a;
+        } else {
+          ++b;
+        }
+      }
+      res[(size_t)c2 * ncol + c1] = acc;
+      res[(size_t)c1 * ncol + c2] = acc;
+    }
+  }
+}
+
 /* RcppSparse.h:145-150 — colSums then true division by Dim[0] (int promoted to double). */
 void oport_colMeans(const int* p, const double* x, int nrow, int ncol, double* means) {
   oport_colSums(p, x, ncol, means);

@@ -4,8 +4,8 @@
 //
 // What is compiled here (sources stay where they lie, nothing is copied):
 //   $(REF)/src/example.cpp            columnSums()            example.cpp:26-32
-//   $(REF)/inst/include/RcppSparse.h  Matrix::{colSums,rowSums,colMeans,rowMeans,
-//                                     transpose,InnerIterator} RcppSparse.h:131-156,218-233,375-385
+//   $(REF)/inst/include/RcppSparse.h  Matrix::{colSums,rowSums,colMeans,rowMeans,crossprod,
+//                                     transpose,InnerIterator} RcppSparse.h:131-194,218-233,375-385
 // against the Rcpp stand-in in oracle/stub/ (R and Rcpp are not installed here).
 //
 // Two things the reference tree does NOT contain, restated below and labelled:
@@ -111,6 +111,17 @@ int oref_rowSums(const int* i, const int* p, const double* x, int nrow, int ncol
   return guarded([&] {
     Rcpp::IntegerVector d;
     copy_out(borrow(i, p, x, nrow, ncol, nnz, d).rowSums(), out);
+  });
+}
+
+// reference RcppSparse.h:158-194, run verbatim (dense n x n result, column-major; the OpenMP pragma is inert:
+// this library is built without -fopenmp).  The reference's inner do-while reads i[] one element past a column's
+// end before testing the bound (:178-180, :182-184); callers pass an i array with one spare element.
+int oref_crossprod(const int* i, const int* p, const double* x, int nrow, int ncol, int64_t nnz, double* out) {
+  return guarded([&] {
+    Rcpp::IntegerVector d;
+    Rcpp::NumericMatrix r = borrow(i, p, x, nrow, ncol, nnz, d).crossprod();
+    if (ncol > 0) std::memcpy(out, r.begin(), sizeof(double) * size_t(ncol) * size_t(ncol));
   });
 }
 

@@ -510,6 +510,68 @@ int sb200_transpose(sb200_matrix* m, int32_t* p_out, int32_t* i_out, double* x_o
   return SB200_OK;
 }
 
+// ---- crossprod (dense A^T A) -------------------------------------------------------------------------------
+// Runs on the row-ordered copy: the cached one of a mirror that owns its arrays (built now if need be), a
+// temporary one otherwise (adopted arrays: the caller may have changed the values since any earlier copy).
+static int crossprod_into(sb200_matrix* m, double* d_res) {
+  const size_t need = sizeof(double) * static_cast<size_t>(m->ncol) * static_cast<size_t>(m->ncol);
+  (void)need;
+  if (m->nnz == 0 || m->nrow == 0) {
+    sb200_matrix empty = *m;
+    empty.nnz = 0;
+    empty.ncol = 0;
+    return launch_crossprod(&empty, m->ncol, d_res, m->stream);
+  }
+  if (m->owns_arrays && m->rows_state != 1) {
+    const int keep = m->rows_state;
+    m->rows_state = 0;
+    build_row_companion(m);
+    if (m->rows_state != 1) m->rows_state = keep;
+  }
+  if (m->rows_state == 1) {
+    m->rows->stream = m->stream;
+    return launch_crossprod(m->rows, m->ncol, d_res, m->stream);
+  }
+  sb200_matrix* t = nullptr;
+  SB_TRY(alloc_matrix(m->device, m->ncol, m->nrow, m->nnz, &t));
+  cudaStreamSynchronize(t->stream);
+  int rc = transpose_device(m, t->d_p, t->d_i, t->d_x);
+  if (rc == SB200_OK) {
+    t->sm_count = m->sm_count;
+    rc = launch_crossprod(t, m->ncol, d_res, m->stream);
+  }
+  if (cudaStreamSynchronize(m->stream) != cudaSuccess && rc == SB200_OK) rc = fail(SB200_E_CUDA, "crossprod: stream sync failed");
+  free_matrix(t);
+  return rc;
+}
+
+int sb200_crossprod_dev(sb200_matrix* m, double* d_out) {
+  ENTER(m);
+  if (m->ncol > 0 && !d_out) return fail(SB200_E_INVALID, "d_out is NULL");
+  return crossprod_into(m, d_out);
+}
+
+int sb200_crossprod(sb200_matrix* m, double* out) {
+  ENTER(m);
+  if (m->ncol == 0) return SB200_OK;
+  if (!out) return fail(SB200_E_INVALID, "output buffer is NULL");
+  const size_t bytes = sizeof(double) * static_cast<size_t>(m->ncol) * static_cast<size_t>(m->ncol);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && bytes > free_b / 2)
+    return fail(SB200_E_NOMEM, "crossprod: the dense ncol x ncol result does not fit on the device");
+  cudaGetLastError();
+  double* d_res = nullptr;
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&d_res), bytes, m->stream));
+  int rc = crossprod_into(m, d_res);
+  if (rc == SB200_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, d_res, bytes, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "crossprod: result copy", __FILE__, __LINE__);
+  }
+  pool_free(d_res, m->stream);
+  return rc;
+}
+
 int sb200_matrix_row_path(sb200_matrix* m, int* banded) {
   ENTER(m);
   if (!banded) return fail(SB200_E_INVALID, "banded is NULL");

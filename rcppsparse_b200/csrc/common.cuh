@@ -139,6 +139,7 @@ int decide_gather_path(sb200_matrix* m);
 int launch_band_gather(sb200_matrix* m, const double* d_v, double* d_out);
 int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out);  // d_v null = rowSums
 void free_matrix_plans(sb200_matrix* m, cudaStream_t s);
+int launch_crossprod(const sb200_matrix* T, int32_t ncol_a, double* d_res, cudaStream_t st);  // crossprod.cu
 int build_row_companion(sb200_matrix* m);  // capi.cu; non-fatal: leaves rows_state = -1 when it cannot be built
 void drop_row_companion(sb200_matrix* m);
 int row_companion_after();                 // SB200_ROW_COMPANION_AFTER (default 8, 0 = never build on its own)

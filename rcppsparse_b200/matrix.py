@@ -172,6 +172,15 @@ class DeviceMatrix:
     def row_means(self, out=None):
         return self._host_vec(_lib.lib().sb200_row_means, self.nrow, out)
 
+    def crossprod(self):
+        """Dense A^T A, (ncol, ncol), exactly symmetric (reference Matrix::crossprod(), RcppSparse.h:158-194)."""
+        out = np.empty((self.ncol, self.ncol), np.float64)
+        check(_lib.lib().sb200_crossprod(self._h, _ptr(out)))
+        return out
+
+    def crossprod_dev(self, d_out) -> None:
+        check(_lib.lib().sb200_crossprod_dev(self._h, _ptr(d_out)))
+
     def spmv(self, v):
         v = np.ascontiguousarray(v, np.float64)
         if v.shape[0] != self.ncol:
@@ -343,6 +352,9 @@ class Matrix:
 
     def rowMeans(self):
         return self._mirror().row_means()
+
+    def crossprod(self):
+        return self._mirror().crossprod()
 
     # ---- A v and A^T v: additions (the reference has only the iterator idiom) -----------------------------
     def spmv(self, v):

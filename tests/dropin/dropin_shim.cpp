@@ -64,6 +64,14 @@ int dropin_reduce(int op, const int* i, const int* p, const double* x, int nrow,
     }
   });
 }
+int dropin_crossprod(const int* i, const int* p, const double* x, int nrow, int ncol, int64_t nnz, double* dst) {
+  return guarded([&] {
+    RcppSparse::Matrix A = view(i, p, x, nrow, ncol, nnz);
+    Rcpp::NumericMatrix r = A.crossprod();
+    if (r.nrow() != ncol || r.ncol() != ncol) throw std::runtime_error("crossprod: wrong shape");
+    if (ncol > 0) std::memcpy(dst, r.begin(), sizeof(double) * size_t(ncol) * size_t(ncol));
+  });
+}
 int dropin_spmv(int transposed, const int* i, const int* p, const double* x, int nrow, int ncol, int64_t nnz,
                 const double* v, double* y) {
   return guarded([&] {

@@ -24,6 +24,7 @@ def shim():
     L.dropin_last_error.restype = C.c_char_p
     L.dropin_reduce.argtypes = [C.c_int, _i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _f64]
     L.dropin_spmv.argtypes = [C.c_int, _i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _f64, _f64]
+    L.dropin_crossprod.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _f64]
     L.dropin_transpose.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _i32, _i32, _f64, _i32]
     L.dropin_alias_semantics.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _f64, _f64]
     L.dropin_repointed_members.argtypes = [_i32, _i32, _f64, _f64, C.c_int, C.c_int, C.c_int64, _f64, _f64]
@@ -69,6 +70,11 @@ def test_dropin_class_matches_golden(shim, golden):
     y = np.empty(ncol)
     assert shim.dropin_spmv(1, i, p, x, nrow, ncol, nnz, g["v_row"], y) == 0, shim.dropin_last_error()
     oracle.assert_within("spmv_t", y, g["spmv_t"], *args, v=g["v_row"])
+    if ncol <= 2000:
+        cp = np.empty((ncol, ncol))
+        assert shim.dropin_crossprod(i, p, x, nrow, ncol, nnz, cp.reshape(-1)) == 0, shim.dropin_last_error()
+        oracle.assert_within("crossprod", cp, oracle.best().crossprod(*args), *args)
+        assert np.array_equal(cp.view(np.uint64), cp.T.view(np.uint64)), "crossprod must be exactly symmetric"
     tp, ti, tx, td = np.empty(nrow + 1, np.int32), np.empty(nnz, np.int32), np.empty(nnz), np.empty(2, np.int32)
     assert shim.dropin_transpose(i, p, x, nrow, ncol, nnz, tp, ti, tx, td) == 0, shim.dropin_last_error()
     assert td.tolist() == [ncol, nrow]

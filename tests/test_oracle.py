@@ -93,3 +93,22 @@ def test_reference_bounds_check_is_an_error_not_ub():
     p = np.array([0, 2], np.int32)
     with pytest.raises(RuntimeError):
         ref.rowSums(i, p, np.ones(2), 3, 1)
+
+
+def test_crossprod_port_equals_reference_and_scipy():
+    """crossprod (reference RcppSparse.h:158-194): the compiled reference, the C port (same merges, same order) and
+    scipy's A.T @ A; the reference's result is exactly symmetric."""
+    import scipy.sparse as sp
+
+    from rcppsparse_b200 import synth
+
+    port = oracle.Port()
+    for spec in (synth.powerlaw_spec(500, 120, 20.0, 3), synth.uniform_spec(300, 64, 0.2, 4), synth.uniform_spec(50, 1, 0.5, 5)):
+        i, p, x = synth.generate_host(spec)
+        a = port.crossprod(i, p, x, spec.nrow, spec.ncol)
+        want = (sp.csc_matrix((x, i, p), shape=(spec.nrow, spec.ncol)).T @ sp.csc_matrix((x, i, p), shape=(spec.nrow, spec.ncol))).toarray()
+        oracle.assert_within("crossprod", a, want, i, p, x, spec.nrow, spec.ncol)
+        assert np.array_equal(a, a.T)
+        if oracle.Ref.available():
+            b = oracle.Ref().crossprod(i, p, x, spec.nrow, spec.ncol)
+            assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), "port and reference must agree bit for bit"

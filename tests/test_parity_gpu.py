@@ -413,6 +413,51 @@ def test_row_companion_golden_edges(golden):
             oracle.assert_within("rowMeans", D.row_means(), g["rowMeans"], *args, tol=TOL)
 
 
+CROSSPROD_CASES = {
+    "C1_cols600": lambda: synth.config("C1", 0.06),                 # 10k rows x 600 columns, 100 per column
+    "powerlaw_rows": lambda: synth.powerlaw_spec(3000, 900, 40.0, 21, row_levels=5),  # popular rows: long row lists
+    "wide_rows": lambda: synth.uniform_spec(40, 1500, 0.5, 22),     # rows of ~750 entries: longer than one staged piece
+    "one_column": lambda: synth.uniform_spec(500, 1, 0.3, 23),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CROSSPROD_CASES))
+def test_crossprod_against_the_reference(case, checker):
+    """Dense A^T A (reference Matrix::crossprod(), RcppSparse.h:158-194) from the row-ordered copy of the mirror:
+    within 1e-12 * sum|a_ri a_rj| of the reference's own merges, and exactly symmetric like its result."""
+    spec = CROSSPROD_CASES[case]()
+    i, p, x = synth.generate_host(spec)
+    args = (i, p, x, spec.nrow, spec.ncol)
+    want = checker.crossprod(*args)
+    with DeviceMatrix.from_host(*args) as D:
+        got = D.crossprod()
+        oracle.assert_within("crossprod", got, want, *args, tol=TOL)
+        assert np.array_equal(bits(got), bits(got.T))
+        assert D.row_path() == "row-companion"  # the copy it was computed from stays with the mirror
+    import torch
+
+    di, dp, dx = (torch.from_numpy(a).cuda() for a in (i, p, x))
+    with DeviceMatrix.adopt(di, dp, dx, spec.nrow, spec.ncol) as A:  # adopted arrays: a temporary copy per call
+        out = torch.empty(spec.ncol * spec.ncol, dtype=torch.float64, device="cuda")
+        A.crossprod_dev(out)
+        A.sync()
+        oracle.assert_within("crossprod", out.cpu().numpy().reshape(spec.ncol, spec.ncol), want, *args, tol=TOL)
+        assert A.row_path() != "row-companion"
+
+
+def test_crossprod_golden_edges(golden, checker):
+    g = golden
+    args = (g["i"], g["p"], g["x"], g["nrow"], g["ncol"])
+    if g["ncol"] > 1500:
+        pytest.skip("dense result too large for an exhaustive check")
+    A = as_matrix(g)
+    got = A.crossprod()
+    assert got.shape == (g["ncol"], g["ncol"])
+    if g["ncol"]:
+        oracle.assert_within("crossprod", got, checker.crossprod(*args), *args, tol=TOL)
+    A.release()
+
+
 def test_host_ops_write_into_caller_buffers():
     """The C ABI writes results through the caller's pointer; the Python mirror exposes that as out=."""
     import torch
