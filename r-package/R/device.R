@@ -31,6 +31,10 @@ b200_transpose <- function(A) {
     if (.b200_is_handle(A)) .Call(`_RcppSparse_b200_dm_transpose`, A$ptr) else .Call(`_RcppSparse_b200_transpose`, A)
 }
 
+b200_crossprod <- function(A) {
+    if (.b200_is_handle(A)) .Call(`_RcppSparse_b200_dm_crossprod`, A$ptr) else .Call(`_RcppSparse_b200_crossprod`, A)
+}
+
 b200_refresh <- function(A) { stopifnot(.b200_is_handle(A)); invisible(.Call(`_RcppSparse_b200_refresh`, A$ptr)) }
 b200_release <- function(A) { stopifnot(.b200_is_handle(A)); invisible(.Call(`_RcppSparse_b200_release`, A$ptr)) }
 

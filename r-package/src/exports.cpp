@@ -38,6 +38,9 @@ Rcpp::NumericVector b200_spmv_t(RcppSparse::Matrix& A, const Rcpp::NumericVector
 //[[Rcpp::export]]
 Rcpp::S4 b200_transpose(RcppSparse::Matrix& A) { return A.transpose().wrap(); }
 
+//[[Rcpp::export]]
+Rcpp::NumericMatrix b200_crossprod(RcppSparse::Matrix& A) { return A.crossprod(); }
+
 // ---- persistent device-resident handle ---------------------------------------------------------------------
 // The external pointer owns a heap Matrix; the Matrix holds Rcpp handles to the dgCMatrix slots (so R keeps them
 // alive) and, after its first sweep, the device mirror.  The finalizer deletes the Matrix, which releases the
@@ -66,6 +69,12 @@ Rcpp::NumericVector b200_dm_sweep(SEXP handle, int op) {
 Rcpp::NumericVector b200_dm_spmv(SEXP handle, const Rcpp::NumericVector& v, bool transposed) {
     MatrixPtr A(handle);
     return transposed ? A->spmv_t(v) : A->spmv(v);
+}
+
+//[[Rcpp::export]]
+Rcpp::NumericMatrix b200_dm_crossprod(SEXP handle) {
+    MatrixPtr A(handle);
+    return A->crossprod();
 }
 
 //[[Rcpp::export]]
