@@ -232,7 +232,7 @@ private:
       if (Dim.size() != 2 || p.size() != long(Dim[1]) + 1 || i.size() != x.size())
         throw std::invalid_argument("RcppSparse::Matrix: slot lengths inconsistent with Dim");
       b200::check(sb200_matrix_create(i.begin(), p.begin(), x.begin(), Dim[0], Dim[1], x.size(),
-                                      b200::device_from_env(), SB200_PIN_HOST, &m.handle));
+                                      b200::device_from_env(), 0u, &m.handle));
       m.src_x = x.begin();
       m.src_i = i.begin();
       m.src_p = p.begin();

@@ -38,7 +38,8 @@ extern "C" {
 #define SB200_E_UNSUPPORTED (-6)
 
 /* flags for sb200_matrix_create* */
-#define SB200_PIN_HOST 1u    /* cudaHostRegister i/p/x for the upload (R-owned memory), unregister after */
+#define SB200_PIN_HOST 1u    /* cudaHostRegister i/x for the upload, unregister after; measured SLOWER than the default
+                                * for pageable memory (pinned-chunk worker threads): 123-170 ms vs 30 ms for 1.2 GB */
 #define SB200_NO_VALIDATE 2u /* skip the structure-validation kernel (trusted producer, benchmarks) */
 #define SB200_NO_ROW_PLAN 4u /* sb200_matrix_create: do not prepare the row-band plan during the upload (column sweeps only) */
 
@@ -55,7 +56,8 @@ int sb200_device_count(int* count);      /* SB200_E_NODEVICE when there is none 
 /* ---- mirror lifecycle -------------------------------------------------------------------
  * sb200_matrix_create: what Exporter::get() / the 4-vector constructor do in the reference
  * (RcppSparse.h:33,417-419) plus the one-time upload.  The host arrays are BORROWED for the
- * duration of the call only (copied to HBM); they may be R-owned (use SB200_PIN_HOST) or
+ * duration of the call only (copied to HBM); they may be R-owned pageable memory (staged through pinned
+ * chunks by worker threads, SB200_COPY_THREADS) or
  * already pinned.  Structure is validated on the device unless SB200_NO_VALIDATE. */
 int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int32_t nrow, int32_t ncol,
                         int64_t nnz, int device, unsigned flags, sb200_matrix** out);

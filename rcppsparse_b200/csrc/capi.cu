@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <thread>
 #include <new>
 #include <string>
 
@@ -278,21 +279,53 @@ int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int
   // histogram of the band plan run on p and i behind their own, shorter copies.
   const bool trace = getenv("SB200_TRACE") != nullptr;
   const auto t0 = std::chrono::steady_clock::now();
+  std::string* x_err_text = nullptr;
+  // Pageable arrays (what R owns) go through the worker threads of hostcopy.cu; pinned or registered ones are
+  // handed to the copy engine directly.
+  const bool stage_i = nnz > 0 && !pinned_i && bi >= STAGED_COPY_MIN_BYTES && host_is_pageable(i);
+  const bool stage_x = nnz > 0 && !pinned_x && bx >= STAGED_COPY_MIN_BYTES && host_is_pageable(x);
   cudaStream_t xs = nullptr;
   cudaError_t e = cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking);
+  int rc = SB200_OK, rc_x = SB200_OK;
+  std::thread x_thread;
+  if (e == cudaSuccess && (stage_i || stage_x)) e = cudaStreamSynchronize(m->stream);  // the arrays exist (allocated in stream order)
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_p, p, bp, cudaMemcpyHostToDevice, m->stream);
-  if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(m->d_i, i, bi, cudaMemcpyHostToDevice, m->stream);
-  if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(m->d_x, x, bx, cudaMemcpyHostToDevice, xs);
-  int rc = SB200_OK;
-  if (e == cudaSuccess) rc = enqueue_finish(m, flags);
+  if (e == cudaSuccess && nnz > 0) {
+    if (stage_i)
+      rc = staged_h2d(device, m->d_i, i, bi);
+    else
+      e = cudaMemcpyAsync(m->d_i, i, bi, cudaMemcpyHostToDevice, m->stream);
+  }
+  if (e == cudaSuccess && rc == SB200_OK && nnz > 0) {
+    if (stage_x) {
+      std::string* err_text = new std::string();
+      x_thread = std::thread([&, err_text] {
+        rc_x = staged_h2d(device, m->d_x, x, bx);
+        if (rc_x != SB200_OK) *err_text = sb200_last_error();  // last_error is per thread
+      });
+      x_err_text = err_text;
+    } else {
+      e = cudaMemcpyAsync(m->d_x, x, bx, cudaMemcpyHostToDevice, xs);
+    }
+  }
+  if (e == cudaSuccess && rc == SB200_OK) rc = enqueue_finish(m, flags);
   if (e == cudaSuccess && rc == SB200_OK && nnz > 0 && m->nrow > 0 && !(flags & SB200_NO_ROW_PLAN)) {
     // plan failures here are not fatal: the row sweeps retry (or fall back to the L2 path) on first use
+    const std::string keep = t_last_error;
     if (decide_row_path(m) == SB200_OK && m->row_path == 1) ensure_scatter_plan(m);
-    set_error("");
+    t_last_error = keep;
   }
   const auto t1 = std::chrono::steady_clock::now();
   if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
   const auto t2 = std::chrono::steady_clock::now();
+  if (x_thread.joinable()) x_thread.join();
+  if (x_err_text) {
+    if (rc == SB200_OK && rc_x != SB200_OK) {
+      rc = rc_x;
+      set_error(*x_err_text);
+    }
+    delete x_err_text;
+  }
   if (xs) {
     const cudaError_t ex = cudaStreamSynchronize(xs);
     if (e == cudaSuccess) e = ex;
@@ -364,7 +397,12 @@ int sb200_matrix_refresh_values(sb200_matrix* m, const double* x) {
   if (m->nnz == 0) return SB200_OK;
   if (!x) return fail(SB200_E_INVALID, "x is NULL");
   drop_row_companion(m);  // its values are the old ones; the call count starts over
-  SB_CUDA(cudaMemcpyAsync(m->d_x, x, sizeof(double) * static_cast<size_t>(m->nnz), cudaMemcpyHostToDevice, m->stream));
+  const size_t bx = sizeof(double) * static_cast<size_t>(m->nnz);
+  if (bx >= STAGED_COPY_MIN_BYTES && host_is_pageable(x)) {
+    SB_CUDA(cudaStreamSynchronize(m->stream));  // nothing on the stream still reads the old values
+    return staged_h2d(m->device, m->d_x, x, bx);
+  }
+  SB_CUDA(cudaMemcpyAsync(m->d_x, x, bx, cudaMemcpyHostToDevice, m->stream));
   SB_CUDA(cudaStreamSynchronize(m->stream));
   return SB200_OK;
 }
@@ -497,12 +535,16 @@ int sb200_transpose(sb200_matrix* m, int32_t* p_out, int32_t* i_out, double* x_o
   int rc = transpose_device(m, t->d_p, t->d_i, t->d_x);
   cudaError_t e = cudaSuccess;
   if (rc == SB200_OK) {
+    const size_t bi = sizeof(int32_t) * static_cast<size_t>(m->nnz), bx = sizeof(double) * static_cast<size_t>(m->nnz);
     e = cudaMemcpyAsync(p_out, t->d_p, sizeof(int32_t) * (static_cast<size_t>(m->nrow) + 1), cudaMemcpyDeviceToHost, m->stream);
-    if (e == cudaSuccess && m->nnz > 0)
-      e = cudaMemcpyAsync(i_out, t->d_i, sizeof(int32_t) * static_cast<size_t>(m->nnz), cudaMemcpyDeviceToHost, m->stream);
-    if (e == cudaSuccess && m->nnz > 0)
-      e = cudaMemcpyAsync(x_out, t->d_x, sizeof(double) * static_cast<size_t>(m->nnz), cudaMemcpyDeviceToHost, m->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    // the result goes back into the caller's (R-allocated, pageable) vectors: through the pinned-chunk workers
+    const bool stage_i = m->nnz > 0 && bi >= STAGED_COPY_MIN_BYTES && host_is_pageable(i_out);
+    const bool stage_x = m->nnz > 0 && bx >= STAGED_COPY_MIN_BYTES && host_is_pageable(x_out);
+    if (e == cudaSuccess && m->nnz > 0 && !stage_i) e = cudaMemcpyAsync(i_out, t->d_i, bi, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess && m->nnz > 0 && !stage_x) e = cudaMemcpyAsync(x_out, t->d_x, bx, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);  // the transposed arrays are complete
+    if (e == cudaSuccess && stage_i) rc = staged_d2h(m->device, i_out, t->d_i, bi);
+    if (e == cudaSuccess && rc == SB200_OK && stage_x) rc = staged_d2h(m->device, x_out, t->d_x, bx);
   }
   free_matrix(t);
   if (rc != SB200_OK) return rc;

@@ -139,6 +139,11 @@ int decide_gather_path(sb200_matrix* m);
 int launch_band_gather(sb200_matrix* m, const double* d_v, double* d_out);
 int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out);  // d_v null = rowSums
 void free_matrix_plans(sb200_matrix* m, cudaStream_t s);
+// hostcopy.cu: pageable host memory through worker threads with pinned chunks (blocking)
+bool host_is_pageable(const void* p);
+int staged_h2d(int device, void* d_dst, const void* h_src, size_t bytes);
+int staged_d2h(int device, void* h_dst, const void* d_src, size_t bytes);
+constexpr size_t STAGED_COPY_MIN_BYTES = 32u << 20;  // below this the driver's own staging is as good
 int launch_crossprod(const sb200_matrix* T, int32_t ncol_a, double* d_res, cudaStream_t st);  // crossprod.cu
 int build_row_companion(sb200_matrix* m);  // capi.cu; non-fatal: leaves rows_state = -1 when it cannot be built
 void drop_row_companion(sb200_matrix* m);

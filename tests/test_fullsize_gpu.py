@@ -61,6 +61,15 @@ def test_c2_full_size_against_the_reference_oracle():
         ri, rp, rx = chk.transpose(*args)
         assert np.array_equal(tp, rp) and np.array_equal(ti, ri)
         assert np.array_equal(tx.view(np.uint64), rx.view(np.uint64))
+        # the same matrix uploaded from PAGEABLE host arrays (what R owns): 1.2 GB through the pinned-chunk workers
+        # (hostcopy.cu); the column sums must be bit-identical to the generated mirror's, and follow a refresh
+        cs = D.col_sums()
+        with DeviceMatrix.from_host(i, p, x, spec.nrow, spec.ncol) as H:
+            assert np.array_equal(H.col_sums().view(np.uint64), cs.view(np.uint64))
+            hi, hp, hx = H.download_columns()
+            assert np.array_equal(hi, i) and np.array_equal(hp, p) and np.array_equal(hx.view(np.uint64), x.view(np.uint64))
+            H.refresh_values(x * 2.0)
+            assert np.array_equal(H.col_sums().view(np.uint64), (cs * 2.0).view(np.uint64))
         # the row sums of a resident mirror move to its row-ordered copy (sparse_b200.h): same bar
         D.row_companion(1)
         assert D.row_path() == "row-companion"
