@@ -279,7 +279,7 @@ int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int
   // histogram of the band plan run on p and i behind their own, shorter copies.
   const bool trace = getenv("SB200_TRACE") != nullptr;
   const auto t0 = std::chrono::steady_clock::now();
-  std::string* x_err_text = nullptr;
+  std::string x_err_text;  // sb200_last_error() is per thread: the values-upload thread reports through this
   // Pageable arrays (what R owns) go through the worker threads of hostcopy.cu; pinned or registered ones are
   // handed to the copy engine directly.
   const bool stage_i = nnz > 0 && !pinned_i && bi >= STAGED_COPY_MIN_BYTES && host_is_pageable(i);
@@ -298,12 +298,10 @@ int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int
   }
   if (e == cudaSuccess && rc == SB200_OK && nnz > 0) {
     if (stage_x) {
-      std::string* err_text = new std::string();
-      x_thread = std::thread([&, err_text] {
+      x_thread = std::thread([&] {
         rc_x = staged_h2d(device, m->d_x, x, bx);
-        if (rc_x != SB200_OK) *err_text = sb200_last_error();  // last_error is per thread
+        if (rc_x != SB200_OK) x_err_text = sb200_last_error();
       });
-      x_err_text = err_text;
     } else {
       e = cudaMemcpyAsync(m->d_x, x, bx, cudaMemcpyHostToDevice, xs);
     }
@@ -319,12 +317,9 @@ int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int
   if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
   const auto t2 = std::chrono::steady_clock::now();
   if (x_thread.joinable()) x_thread.join();
-  if (x_err_text) {
-    if (rc == SB200_OK && rc_x != SB200_OK) {
-      rc = rc_x;
-      set_error(*x_err_text);
-    }
-    delete x_err_text;
+  if (rc == SB200_OK && rc_x != SB200_OK) {
+    rc = rc_x;
+    set_error(x_err_text);
   }
   if (xs) {
     const cudaError_t ex = cudaStreamSynchronize(xs);
@@ -556,13 +551,10 @@ int sb200_transpose(sb200_matrix* m, int32_t* p_out, int32_t* i_out, double* x_o
 // Runs on the row-ordered copy: the cached one of a mirror that owns its arrays (built now if need be), a
 // temporary one otherwise (adopted arrays: the caller may have changed the values since any earlier copy).
 static int crossprod_into(sb200_matrix* m, double* d_res) {
-  const size_t need = sizeof(double) * static_cast<size_t>(m->ncol) * static_cast<size_t>(m->ncol);
-  (void)need;
-  if (m->nnz == 0 || m->nrow == 0) {
-    sb200_matrix empty = *m;
-    empty.nnz = 0;
-    empty.ncol = 0;
-    return launch_crossprod(&empty, m->ncol, d_res, m->stream);
+  if (m->nnz == 0 || m->nrow == 0) {  // no products at all: the result is the zero matrix
+    if (m->ncol > 0)
+      SB_CUDA(cudaMemsetAsync(d_res, 0, sizeof(double) * static_cast<size_t>(m->ncol) * static_cast<size_t>(m->ncol), m->stream));
+    return SB200_OK;
   }
   if (m->owns_arrays && m->rows_state != 1) {
     const int keep = m->rows_state;

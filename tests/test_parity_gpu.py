@@ -4,6 +4,8 @@ ones include/RcppSparse.h calls), against the oracle on identical inputs.
 Bar (BASELINE.json north_star): transpose structure p/i and the permuted values bit-exact;
 FP64 reductions within |delta| <= 1e-12 * sum|a_ij| (|a_ij * v_j| for SpMV) per output entry.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -456,6 +458,42 @@ def test_crossprod_golden_edges(golden, checker):
     if g["ncol"]:
         oracle.assert_within("crossprod", got, checker.crossprod(*args), *args, tol=TOL)
     A.release()
+
+
+@pytest.mark.parametrize("threads", ["1", "default"])
+def test_pageable_arrays_travel_through_the_pinned_chunk_workers(threads, checker):
+    """Arrays of 32 MB and more in ordinary (pageable) host memory — what R owns — are staged through pinned chunks by
+    worker threads in both directions (hostcopy.cu): upload at create and refresh, download of a transposed result.
+    Bitwise round trips; chunk boundaries (8 MB) fall inside the arrays many times."""
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np\n"
+        "from oracle import oracle\n"
+        "from rcppsparse_b200 import DeviceMatrix, synth\n"
+        "spec = synth.config('C2', 0.09)\n"  # 9e6 entries: i 36 MB, x 72 MB
+        "i, p, x = synth.generate_host(spec)\n"
+        "assert i.nbytes >= 32 << 20 and x.nbytes >= 32 << 20\n"
+        "chk = oracle.best()\n"
+        "args = (i, p, x, spec.nrow, spec.ncol)\n"
+        "with DeviceMatrix.from_host(*args) as D:\n"
+        "    di, dp, dx = D.download_columns()\n"
+        "    assert np.array_equal(di, i) and np.array_equal(dp, p) and np.array_equal(dx.view(np.uint64), x.view(np.uint64))\n"
+        "    oracle.assert_within('colSums', D.col_sums(), chk.colSums(*args), *args)\n"
+        "    ti, tp, tx = D.transpose_host()\n"
+        "    ri, rp, rx = chk.transpose(*args)\n"
+        "    assert np.array_equal(tp, rp) and np.array_equal(ti, ri) and np.array_equal(tx.view(np.uint64), rx.view(np.uint64))\n"
+        "    x2 = x[::-1].copy()\n"
+        "    D.refresh_values(x2)\n"
+        "    assert np.array_equal(D.download_columns()[2].view(np.uint64), x2.view(np.uint64))\n"
+        "print('ok')\n")
+    env = dict(os.environ)
+    if threads != "default":
+        env["SB200_COPY_THREADS"] = threads  # read once per process: hence the subprocess
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
 
 
 def test_host_ops_write_into_caller_buffers():
