@@ -63,6 +63,9 @@ __device__ __forceinline__ void xg_signal_and_wait(const XgPeers& peers, int ran
   __threadfence_system();
   st_release_sys(reinterpret_cast<uint32_t*>(peers.base[q]) + rank, epoch);
   const uint32_t* mine = reinterpret_cast<const uint32_t*>(peers.base[rank]) + q;
+  // once a wait has given up, later barriers do not wait again (a dead peer must not cost 4 s per call);
+  // sb200_exchange_status reports the failure
+  if (*reinterpret_cast<volatile uint32_t*>(peers.base[rank] + 4 * XG_W_ERROR) != 0u) return;
   const long long t0 = clock64();
   while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) {
     if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz: a peer is gone
