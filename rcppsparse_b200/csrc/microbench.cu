@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+
+#include <string>
 #include <stdlib.h>
 
 #define CK(x)                                                                                  \
@@ -158,6 +160,38 @@ static float time_it(F f, int reps) {
   return best;
 }
 
+// G consecutive doubles at a pseudo-random G-aligned place of an n-double region: what a scattered store of
+// 8 / 32 / 128 bytes costs per byte (the transpose writes 4 + 8 bytes per entry to unrelated sectors)
+template <int G>
+__global__ void scatter_store_kernel(double* __restrict__ out, int64_t n) {
+  const int64_t groups = n / G;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < groups; k += stride) {
+    const int64_t g = static_cast<int64_t>(mix64(static_cast<uint64_t>(k)) % static_cast<uint64_t>(groups));
+    double* dst = out + g * G;
+#pragma unroll
+    for (int t = 0; t < G; t += 2) *reinterpret_cast<double2*>(dst + t) = make_double2(1.0 + k, 2.0);
+  }
+}
+template <>
+__global__ void scatter_store_kernel<1>(double* __restrict__ out, int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride)
+    out[static_cast<int64_t>(mix64(static_cast<uint64_t>(k)) % static_cast<uint64_t>(n))] = 1.0 + k;
+}
+
+// F append fronts (output rows), every entry goes to the next free slot of a pseudo-random front: each 32-byte
+// sector receives its 4 doubles at 4 far-apart times, like the rows of a transposed matrix
+__global__ void front_store_kernel(double* __restrict__ out, int64_t n, int64_t fronts) {
+  const int64_t per = n / fronts;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < per * fronts; k += stride) {
+    const int64_t round = k / fronts;  // all fronts advance together: slot `round` of front f
+    const int64_t f = static_cast<int64_t>(mix64(static_cast<uint64_t>(k)) % static_cast<uint64_t>(fronts));
+    out[f * per + round] = 1.0 + k;
+  }
+}
+
 int main(int argc, char** argv) {
   const int64_t n = argc > 1 ? atoll(argv[1]) : 100000000LL;
   const int32_t rows = argc > 2 ? atoi(argv[2]) : 1000000;
@@ -180,6 +214,22 @@ int main(int argc, char** argv) {
   CK(cudaDeviceSynchronize());
   const int64_t n4 = n / 4, n2 = n / 2;
   const int reps = 5;
+  if (argc > 3 && std::string(argv[3]) == "stores") {
+    const int grid = sms * 8;
+    float ms = time_it([&] { scatter_store_kernel<1><<<grid, 256>>>(val2, n); }, reps);
+    printf("{\"test\":\"scatter_store\",\"bytes_per_store\":8,\"ms\":%.4f,\"GBps\":%.1f}\n", ms, n * 8.0 / ms / 1e6);
+    ms = time_it([&] { scatter_store_kernel<2><<<grid, 256>>>(val2, n); }, reps);
+    printf("{\"test\":\"scatter_store\",\"bytes_per_store\":16,\"ms\":%.4f,\"GBps\":%.1f}\n", ms, n * 8.0 / ms / 1e6);
+    ms = time_it([&] { scatter_store_kernel<4><<<grid, 256>>>(val2, n); }, reps);
+    printf("{\"test\":\"scatter_store\",\"bytes_per_store\":32,\"ms\":%.4f,\"GBps\":%.1f}\n", ms, n * 8.0 / ms / 1e6);
+    ms = time_it([&] { scatter_store_kernel<16><<<grid, 256>>>(val2, n); }, reps);
+    printf("{\"test\":\"scatter_store\",\"bytes_per_store\":128,\"ms\":%.4f,\"GBps\":%.1f}\n", ms, n * 8.0 / ms / 1e6);
+    for (int64_t fronts : {1000LL, 30000LL, 180000LL, 1000000LL, 10000000LL}) {
+      ms = time_it([&] { front_store_kernel<<<grid, 256>>>(val2, n, fronts); }, reps);
+      printf("{\"test\":\"front_store\",\"fronts\":%lld,\"ms\":%.4f,\"GBps\":%.1f}\n", (long long)fronts, ms, n * 8.0 / ms / 1e6);
+    }
+    return 0;
+  }
   for (int mult = 4; mult <= 16; mult *= 2) {
     const int grid = sms * mult;
     float ms = time_it([&] { read_kernel<<<grid, 256>>>((const double2*)val, n2, out); }, reps);
