@@ -75,6 +75,14 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def value_before_row_copy(ops, nnz, per_op_ms, scatter_ms):
+    """Throughput of the same step with rowSums/rowMeans still on the scatter kernels (a mirror's first 8 row-sum
+    calls, and adopted device arrays): the timed ops' own times, with each row op replaced by the scatter time
+    measured before the row-ordered copy was built."""
+    total_ms = sum(scatter_ms if op in ("rowSums", "rowMeans") else per_op_ms[op] for op in ops)
+    return len(ops) * nnz / (total_ms * 1e-3) if total_ms > 0 else None
+
+
 def profile_traffic(kernel):
     """dram bytes per launch of `kernel` at the default workload from the committed ncu capture, if any."""
     path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
@@ -400,6 +408,8 @@ def run_b200(args, ops):
                 "traffic": profile_traffic(dom_kernel) if (args.workload, args.scale) == ("C2", 1.0) else None}
     if row_companion is not None:
         row_companion["scatter_frac_of_measured"] = row_companion["scatter_GBps"] / peak
+        if world == 1 and row_companion.get("built"):
+            row_companion["value_before_row_copy"] = value_before_row_copy(ops, nnz, per_op_ms, row_companion["scatter_ms_per_call"])
 
     line = {
         "metric": METRIC, "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -44,3 +44,18 @@ def test_cuda_arm_refuses_to_run_without_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_value_before_row_copy_arithmetic():
+    """bench.py reports, next to the steady-state value, what the same step does while the row sums are still on
+    the scatter kernels; the helper only swaps the row ops' times."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ops = ("colSums", "rowSums", "colMeans", "rowMeans")
+    per_op = {"colSums": 0.1, "rowSums": 0.1, "colMeans": 0.1, "rowMeans": 0.1}
+    v = mod.value_before_row_copy(ops, 10**8, per_op, 0.5)
+    assert abs(v - 4e8 / 1.2e-3) < 1e-3 * v
+    assert mod.value_before_row_copy(("colSums",), 10**8, per_op, 0.5) == 1e8 / 1e-4
