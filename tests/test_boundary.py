@@ -117,3 +117,20 @@ def test_r_package_entry_points_consistent():
     defined = set(re.findall(r"^(\w+)\s*<-\s*function", r_code, flags=re.M))
     assert exported and exported <= defined, exported - defined
     assert "useDynLib(RcppSparse, .registration = TRUE)" in namespace
+
+
+def test_r_package_call_table_is_what_the_generator_writes(tmp_path, monkeypatch):
+    """src/RcppExports.cpp is generated from the //[[Rcpp::export]] tags (tools/gen_rcpp_exports.py stands in for
+    Rcpp::compileAttributes()); the committed file must be up to date."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("gen", os.path.join(ROOT, "tools", "gen_rcpp_exports.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    committed = open(os.path.join(ROOT, "r-package", "src", "RcppExports.cpp")).read()
+    src = tmp_path / "src"
+    src.mkdir()
+    (src / "exports.cpp").write_text(open(os.path.join(ROOT, "r-package", "src", "exports.cpp")).read())
+    monkeypatch.setattr(gen, "SRC", str(src))
+    gen.main()
+    assert (src / "RcppExports.cpp").read_text() == committed
