@@ -117,13 +117,19 @@ class PeerWindow:
         from . import _lib
         self._lib, self.device, self.rank, self.world = _lib, device, rank, world
         self._h = C.c_void_p()
+        self.side = None
         handle = (C.c_ubyte * 64)()
-        _lib.check(_lib.lib().sb200_exchange_create(device.index, int(data_bytes) + 4096, C.byref(self._h), handle))
-        gathered = [None] * world
-        dist.all_gather_object(gathered, bytes(handle), group=group)
-        blob = b"".join(gathered)
-        rc = _lib.lib().sb200_exchange_connect(self._h, rank, world, blob)
+        # every rank goes through both collectives below whatever happened locally, so a rank that cannot create
+        # or map a window never leaves the others waiting
+        rc = _lib.lib().sb200_exchange_create(device.index, int(data_bytes) + 4096, C.byref(self._h), handle)
         err = _lib.lib().sb200_last_error().decode(errors="replace") if rc != 0 else ""
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bytes(handle) if rc == 0 else None, group=group)
+        if rc == 0 and all(g is not None for g in gathered):
+            rc = _lib.lib().sb200_exchange_connect(self._h, rank, world, b"".join(gathered))
+            err = _lib.lib().sb200_last_error().decode(errors="replace") if rc != 0 else ""
+        elif rc == 0:
+            rc, err = -1, "a peer could not create its window"
         ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
         if int(ok.item()) == 0:  # some rank could not map its peers: nobody uses the window
@@ -132,7 +138,6 @@ class PeerWindow:
         base, off, nbytes = C.c_void_p(), C.c_int64(), C.c_int64()
         _lib.check(_lib.lib().sb200_exchange_window(self._h, C.byref(base), C.byref(off), C.byref(nbytes)))
         self.base, self._cursor, self.bytes = base.value, off.value, nbytes.value
-        self.side = None
 
     def alloc(self, n: int):
         """(byte offset, float64 tensor of n entries) inside the window; 256-byte aligned."""

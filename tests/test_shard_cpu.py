@@ -131,3 +131,53 @@ def test_split_handles_degenerate_matrices():
     assert shard.split_columns_by_nnz(np.zeros(1, np.int32), 4) == [0, 0, 0, 0, 0]       # ncol = 0
     assert shard.split_columns_by_nnz(np.zeros(6, np.int32), 2) == [0, 0, 5]             # all columns empty
     assert shard.split_columns_evenly(10, 4) == [0, 2, 5, 7, 10]
+
+
+class _FakeExchangeLib:
+    """Stands in for libsparse_b200's exchange entry points so that PeerWindow's handshake can run without a GPU."""
+
+    def __init__(self, create_rc=0, connect_rc=0):
+        self.create_rc, self.connect_rc, self.calls = create_rc, connect_rc, []
+
+    def sb200_exchange_create(self, device, nbytes, out_handle, ipc):
+        self.calls.append("create")
+        if self.create_rc == 0:
+            out_handle._obj.value = 0x1234
+        return self.create_rc
+
+    def sb200_exchange_connect(self, h, rank, world, blob):
+        self.calls.append(("connect", rank, world, len(blob)))
+        return self.connect_rc
+
+    def sb200_exchange_window(self, h, base, off, nbytes):
+        base._obj.value, off._obj.value, nbytes._obj.value = 1 << 20, 4096, 1 << 16
+        return 0
+
+    def sb200_exchange_destroy(self, h):
+        self.calls.append("destroy")
+        return 0
+
+    def sb200_last_error(self):
+        return b"fake failure"
+
+
+@pytest.mark.parametrize("create_rc,connect_rc,ok", [(0, 0, True), (5, 0, False), (0, 5, False)])
+def test_peer_window_handshake_never_strands_a_rank(create_rc, connect_rc, ok, monkeypatch):
+    """Whatever fails locally (creating the window, mapping a peer), a rank still takes part in both collectives of
+    the handshake and then every rank raises together — nobody is left waiting in a collective."""
+    from rcppsparse_b200 import _lib
+
+    fake = _FakeExchangeLib(create_rc, connect_rc)
+    monkeypatch.setattr(_lib, "lib", lambda: fake)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(_free_port())
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        if ok:
+            W = shard.PeerWindow(torch.device("cpu"), 0, 1, 1 << 12)
+            assert fake.calls[:2] == ["create", ("connect", 0, 1, 64)] and W.bytes == 1 << 16
+        else:
+            with pytest.raises(RuntimeError, match="peer window not available"):
+                shard.PeerWindow(torch.device("cpu"), 0, 1, 1 << 12)
+            assert "destroy" in fake.calls or create_rc != 0
+    finally:
+        dist.destroy_process_group()
