@@ -248,10 +248,16 @@ class ShardedMatrix:
 
     def close(self) -> None:
         if self.window is not None:
-            self.window.status()
+            failure = None
+            try:
+                self.window.status()
+            except Exception as e:  # reported after the collective below: the other ranks are waiting in it
+                failure = e
             dist.barrier(group=self.group)  # nobody unmaps while a peer may still write
             self.window.close()
             self.window = None
+            if failure is not None:
+                raise failure
 
     # ---- p2p path: results live in the window ------------------------------------------------------------------
     def _window_cols(self, name: str):
