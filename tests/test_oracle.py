@@ -112,3 +112,20 @@ def test_crossprod_port_equals_reference_and_scipy():
         if oracle.Ref.available():
             b = oracle.Ref().crossprod(i, p, x, spec.nrow, spec.ncol)
             assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), "port and reference must agree bit for bit"
+
+
+def test_crossprod_known_answer_on_the_vignette_matrix():
+    """The one literal matrix in the reference tree (vignettes/Documentation.Rmd:213-216), A^T A worked out by hand."""
+    x = np.array([0.41, 0.35, 0.84, 0.37, 0.26])
+    i = np.array([0, 2, 0, 1, 1], np.int32)
+    p = np.array([0, 0, 1, 2, 4, 5], np.int32)
+    want = np.zeros((5, 5))
+    want[1, 1] = 0.41 * 0.41
+    want[1, 3] = want[3, 1] = 0.41 * 0.84
+    want[2, 2] = 0.35 * 0.35
+    want[3, 3] = 0.84 * 0.84 + 0.37 * 0.37
+    want[3, 4] = want[4, 3] = 0.37 * 0.26
+    want[4, 4] = 0.26 * 0.26
+    for chk in ([oracle.Port()] + ([oracle.Ref()] if oracle.Ref.available() else [])):
+        got = chk.crossprod(i, p, x, 5, 5)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), chk.kind
