@@ -14,8 +14,9 @@
 //   Rcpp::traits::Exporter<RcppSparse::Matrix>             reference :398-423
 // Additions: spmv(v) = A v and spmv_t(v) = A^T v (the reference only has the iterator idiom),
 // refresh() after mutating x in place, release() to drop the device mirror early.
-// Not provided here (off the hot path): the range/row iterators,
-// dense block extraction, isAppxSymmetric, InnerIndices.
+//   dense copies (operator()(rows, cols), col, row), InnerIndices, emptyInnerIndices, isAppxSymmetric,
+//   InnerIteratorInRange / NotInRange, InnerRowIterator       reference :75-128, :196-216, :238-373 (host side; the
+//   row iterator and the symmetry test do what their interfaces promise — the reference's own walk is broken)
 //
 // Include order: like the reference, this header must come BEFORE <Rcpp.h> in a translation unit
 // (it forward-declares the Exporter specialisation between <RcppCommon.h> and <Rcpp.h>).
@@ -39,6 +40,7 @@ class Exporter<RcppSparse::Matrix>;
 
 #include <cstdlib>
 #include <memory>
+#include <vector>
 #include <stdexcept>
 #include <string>
 
@@ -128,6 +130,86 @@ public:
   double operator()(int row, int col) const { return at(row, col); }
   double operator[](int index) const { return x[index]; }
 
+  // ---- dense copies of parts of the matrix (reference :75-128; host side, same signatures) -------------
+  // one row of selected columns, one column of selected rows, a block
+  Rcpp::NumericVector operator()(int row, Rcpp::IntegerVector& col) {
+    Rcpp::NumericVector out(col.size());
+    for (long k = 0; k < col.size(); ++k) out[k] = at(row, col[k]);
+    return out;
+  }
+  Rcpp::NumericVector operator()(Rcpp::IntegerVector& row, int col) {
+    Rcpp::NumericVector out(row.size());
+    for (long k = 0; k < row.size(); ++k) out[k] = at(row[k], col);
+    return out;
+  }
+  Rcpp::NumericMatrix operator()(Rcpp::IntegerVector& row, Rcpp::IntegerVector& col) {
+    Rcpp::NumericMatrix out(row.size(), col.size());
+    for (long c = 0; c < col.size(); ++c)
+      for (long r = 0; r < row.size(); ++r) out(r, c) = at(row[r], col[c]);
+    return out;
+  }
+  // a column as a dense vector: scatter the stored entries over zeros
+  Rcpp::NumericVector col(int c) {
+    Rcpp::NumericVector dense(Dim[0]);
+    for (int k = p[c], end = p[c + 1]; k < end; ++k) dense[i[k]] = x[k];
+    return dense;
+  }
+  Rcpp::NumericMatrix col(Rcpp::IntegerVector& c) {
+    Rcpp::NumericMatrix out(Dim[0], c.size());
+    for (long j = 0; j < c.size(); ++j)
+      for (int k = p[c[j]], end = p[c[j] + 1]; k < end; ++k) out(i[k], j) = x[k];
+    return out;
+  }
+  // a row as a dense vector: one sorted lookup per column
+  Rcpp::NumericVector row(int r) {
+    Rcpp::NumericVector dense(Dim[1]);
+    for (int c = 0; c < Dim[1]; ++c) {
+      const int k = find_in_column(c, r);
+      if (k >= 0) dense[c] = x[k];
+    }
+    return dense;
+  }
+  Rcpp::NumericMatrix row(Rcpp::IntegerVector& r) {
+    Rcpp::NumericMatrix out(r.size(), Dim[1]);
+    for (int c = 0; c < Dim[1]; ++c)
+      for (long j = 0; j < r.size(); ++j) {
+        const int k = find_in_column(c, r[j]);
+        if (k >= 0) out(j, c) = x[k];
+      }
+    return out;
+  }
+
+  // rows with / without a stored entry in a column (reference :196-216)
+  std::vector<unsigned int> InnerIndices(int col) {
+    std::vector<unsigned int> rows_of;
+    rows_of.reserve(p[col + 1] - p[col]);
+    for (int k = p[col], end = p[col + 1]; k < end; ++k) rows_of.push_back(static_cast<unsigned int>(i[k]));
+    return rows_of;
+  }
+  std::vector<unsigned int> emptyInnerIndices(int col) {
+    std::vector<unsigned int> rows_without;
+    rows_without.reserve(Dim[0] - (p[col + 1] - p[col]));
+    int k = p[col];
+    const int end = p[col + 1];
+    for (int r = 0; r < Dim[0]; ++r) {
+      if (k < end && i[k] == r)
+        ++k;
+      else
+        rows_without.push_back(static_cast<unsigned int>(r));
+    }
+    return rows_without;
+  }
+
+  // A(r, c) == A(c, r) for every stored entry of a square matrix (what the reference's isAppxSymmetric, :362-373,
+  // sets out to test; its own loop only compares the first column with a mis-walked first row)
+  bool isAppxSymmetric() {
+    if (Dim[0] != Dim[1]) return false;
+    for (int c = 0; c < Dim[1]; ++c)
+      for (int k = p[c], end = p[c + 1]; k < end; ++k)
+        if (at(c, i[k]) != x[k]) return false;
+    return true;
+  }
+
   // ---- the sweeps: one kernel launch each behind the C ABI --------------------------------------------
   Rcpp::NumericVector colSums() {
     Rcpp::NumericVector sums(Dim[1]);
@@ -216,7 +298,114 @@ public:
     int col_, at_, end_;
   };
 
+  // ---- stored entries of a column whose rows are (not) in a sorted list (reference :238-321, host side) ----
+  // Same protocol as InnerIterator.  `rows` must be ascending; it is only read.  Two cursors advance in step
+  // over the column's sorted rows and the list until they meet (InRange) / over the column skipping rows that
+  // the list contains (NotInRange).
+  class InnerIteratorInRange {
+  public:
+    InnerIteratorInRange(Matrix& m, int col, std::vector<unsigned int>& rows)
+        : m_(m), rows_(rows), col_(col), at_(m.p[col]), end_(m.p[col + 1]), s_(0) {
+      settle();
+    }
+    operator bool() const { return at_ < end_ && s_ < rows_.size(); }
+    InnerIteratorInRange& operator++() {
+      ++at_;
+      ++s_;
+      settle();
+      return *this;
+    }
+    const double& value() const { return m_.x[at_]; }
+    int row() const { return m_.i[at_]; }
+    int col() const { return col_; }
+
+  private:
+    void settle() {  // advance whichever cursor is behind until both name the same row
+      while (at_ < end_ && s_ < rows_.size()) {
+        const unsigned int r = static_cast<unsigned int>(m_.i[at_]);
+        if (r == rows_[s_]) return;
+        if (r < rows_[s_])
+          ++at_;
+        else
+          ++s_;
+      }
+    }
+    Matrix& m_;
+    const std::vector<unsigned int>& rows_;
+    int col_, at_, end_;
+    size_t s_;
+  };
+
+  class InnerIteratorNotInRange {
+  public:
+    InnerIteratorNotInRange(Matrix& m, int col, std::vector<unsigned int>& rows)
+        : m_(m), rows_(rows), col_(col), at_(m.p[col]), end_(m.p[col + 1]), s_(0) {
+      settle();
+    }
+    operator bool() const { return at_ < end_; }
+    InnerIteratorNotInRange& operator++() {
+      ++at_;
+      settle();
+      return *this;
+    }
+    const double& value() const { return m_.x[at_]; }
+    int row() const { return m_.i[at_]; }
+    int col() const { return col_; }
+
+  private:
+    void settle() {  // skip stored entries whose row the list contains
+      while (at_ < end_) {
+        const unsigned int r = static_cast<unsigned int>(m_.i[at_]);
+        while (s_ < rows_.size() && rows_[s_] < r) ++s_;
+        if (s_ < rows_.size() && rows_[s_] == r)
+          ++at_;
+        else
+          return;
+      }
+    }
+    Matrix& m_;
+    const std::vector<unsigned int>& rows_;
+    int col_, at_, end_;
+    size_t s_;
+  };
+
+  // ---- stored entries of one row, in column order (reference :324-354; host side).  The reference's version
+  // scans i[] as if it were laid out by row; this one does what its interface promises: a sorted lookup in each
+  // column, cost O(ncol log(column length)).  For many rows use transpose() once instead. ----
+  class InnerRowIterator {
+  public:
+    InnerRowIterator(Matrix& m, int row) : m_(m), row_(row), col_(-1), at_(-1) { ++(*this); }
+    operator bool() const { return col_ < m_.Dim[1]; }
+    InnerRowIterator& operator++() {
+      for (++col_; col_ < m_.Dim[1]; ++col_) {
+        at_ = m_.find_in_column(col_, row_);
+        if (at_ >= 0) break;
+      }
+      return *this;
+    }
+    double& value() const { return m_.x[at_]; }
+    int row() const { return row_; }
+    int col() const { return col_; }
+
+  private:
+    Matrix& m_;
+    int row_, col_, at_;
+  };
+
 private:
+  // position of (row, col) in x / i, or -1: binary search in the column's sorted rows
+  int find_in_column(int col, int row) const {
+    int lo = p[col], hi = p[col + 1];
+    while (lo < hi) {
+      const int mid = lo + (hi - lo) / 2;
+      if (i[mid] < row)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    return (lo < p[col + 1] && i[lo] == row) ? lo : -1;
+  }
+
   // Created with the object (empty), so that copies made at any time share one holder: a copy of a
   // Matrix aliases the same R vectors and must see the same device state.
   std::shared_ptr<b200::Mirror> mirror_;

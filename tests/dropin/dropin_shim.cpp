@@ -6,7 +6,9 @@
 
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <vector>
 
 // The package's exported function (reference src/example.cpp:26-32) in the drop-in build: the sweep is
 // one call on the class instead of a serial InnerIterator loop.
@@ -122,6 +124,70 @@ int dropin_repointed_members(const int* i, const int* p, const double* x1, const
     out(A.colSums(), sums1);
     A.x = Rcpp::NumericVector::view(const_cast<double*>(x2), long(nnz));  // another vector: new upload
     out(A.colSums(), sums2);
+  });
+}
+// ---- host-side accessors and cursors (no device involved) ---------------------------------------------------
+int dropin_dense_parts(const int* i, const int* p, const double* x, int nrow, int ncol, int64_t nnz, int r, int c,
+                       const int* rows, int nrows, const int* cols, int ncols, double* row_out, double* col_out,
+                       double* block_out, double* rowsel_out, double* colsel_out, double* cols_out, double* rows_out) {
+  return guarded([&] {
+    RcppSparse::Matrix A = view(i, p, x, nrow, ncol, nnz);
+    Rcpp::IntegerVector rv = Rcpp::IntegerVector::view(const_cast<int*>(rows), nrows);
+    Rcpp::IntegerVector cv = Rcpp::IntegerVector::view(const_cast<int*>(cols), ncols);
+    out(A.row(r), row_out);
+    out(A.col(c), col_out);
+    out(A(r, cv), rowsel_out);
+    out(A(rv, c), colsel_out);
+    Rcpp::NumericMatrix b = A(rv, cv);
+    for (int k = 0; k < ncols; ++k)
+      for (int j = 0; j < nrows; ++j) block_out[size_t(k) * nrows + j] = b(j, k);
+    Rcpp::NumericMatrix cm = A.col(cv);  // nrow x ncols
+    for (int k = 0; k < ncols; ++k)
+      for (int j = 0; j < nrow; ++j) cols_out[size_t(k) * nrow + j] = cm(j, k);
+    Rcpp::NumericMatrix rm = A.row(rv);  // nrows x ncol
+    for (int k = 0; k < ncol; ++k)
+      for (int j = 0; j < nrows; ++j) rows_out[size_t(k) * nrows + j] = rm(j, k);
+  });
+}
+// entries of column `col` whose rows are in / not in the sorted list s; the rows with / without an entry
+int dropin_range_cursors(const int* i, const int* p, const double* x, int nrow, int ncol, int64_t nnz, int col,
+                         const unsigned* s, int ns, int* in_rows, double* in_vals, int* n_in, int* out_rows,
+                         double* out_vals, int* n_out, unsigned* inner, int* n_inner, unsigned* empty, int* n_empty) {
+  return guarded([&] {
+    RcppSparse::Matrix A = view(i, p, x, nrow, ncol, nnz);
+    std::vector<unsigned int> sv(s, s + ns);
+    int k = 0;
+    for (RcppSparse::Matrix::InnerIteratorInRange it(A, col, sv); it; ++it, ++k) {
+      if (it.col() != col) throw std::runtime_error("InRange: col()");
+      in_rows[k] = it.row();
+      in_vals[k] = it.value();
+    }
+    *n_in = k;
+    k = 0;
+    for (RcppSparse::Matrix::InnerIteratorNotInRange it(A, col, sv); it; ++it, ++k) {
+      out_rows[k] = it.row();
+      out_vals[k] = it.value();
+    }
+    *n_out = k;
+    std::vector<unsigned int> a = A.InnerIndices(col), e = A.emptyInnerIndices(col);
+    std::copy(a.begin(), a.end(), inner);
+    std::copy(e.begin(), e.end(), empty);
+    *n_inner = int(a.size());
+    *n_empty = int(e.size());
+  });
+}
+int dropin_row_cursor(const int* i, const int* p, const double* x, int nrow, int ncol, int64_t nnz, int row, int* cols,
+                      double* vals, int* n, int* symmetric) {
+  return guarded([&] {
+    RcppSparse::Matrix A = view(i, p, x, nrow, ncol, nnz);
+    int k = 0;
+    for (RcppSparse::Matrix::InnerRowIterator it(A, row); it; ++it, ++k) {
+      if (it.row() != row) throw std::runtime_error("InnerRowIterator: row()");
+      cols[k] = it.col();
+      vals[k] = it.value();
+    }
+    *n = k;
+    *symmetric = A.isAppxSymmetric() ? 1 : 0;
   });
 }
 int dropin_missing_slot() {

@@ -24,6 +24,13 @@ def shim():
     L.dropin_last_error.restype = C.c_char_p
     L.dropin_reduce.argtypes = [C.c_int, _i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _f64]
     L.dropin_spmv.argtypes = [C.c_int, _i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _f64, _f64]
+    _u32 = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+    _ip = C.POINTER(C.c_int)
+    L.dropin_dense_parts.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, _i32, C.c_int, _i32, C.c_int,
+                                     _f64, _f64, _f64, _f64, _f64, _f64, _f64]
+    L.dropin_range_cursors.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, C.c_int, _u32, C.c_int, _i32, _f64, _ip,
+                                       _i32, _f64, _ip, _u32, _ip, _u32, _ip]
+    L.dropin_row_cursor.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, C.c_int, _i32, _f64, _ip, _ip]
     L.dropin_crossprod.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _f64]
     L.dropin_transpose.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _i32, _i32, _f64, _i32]
     L.dropin_alias_semantics.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _f64, _f64]
@@ -124,3 +131,79 @@ def test_r_package_glue_type_checks():
                         "-include", os.path.join(root, "tests", "dropin", "rcpp_xptr_stub.h"),
                         os.path.join(root, "r-package", "src", "exports.cpp")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def _small_matrix(seed, nrow=23, ncol=17, density=0.3, symmetric=False):
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(seed)
+    dense = np.where(rng.random((nrow, ncol)) < density, np.round(rng.standard_normal((nrow, ncol)), 2), 0.0)
+    dense[:, 3] = 0.0  # an empty column
+    dense[5, :] = 0.0  # an empty row
+    if symmetric:
+        dense = np.triu(dense[:ncol, :ncol]) + np.triu(dense[:ncol, :ncol], 1).T
+    A = sp.csc_matrix(dense)
+    A.sort_indices()
+    return dense, A.indices.astype(np.int32), A.indptr.astype(np.int32), A.data.astype(np.float64)
+
+
+def test_dropin_host_side_dense_parts(shim):
+    """Dense copies of rows, columns and blocks (reference RcppSparse.h:75-128) are host-side lookups: no GPU."""
+    dense, i, p, x = _small_matrix(1)
+    nrow, ncol = dense.shape
+    rows, cols = np.array([0, 5, 22, 7, 7], np.int32), np.array([3, 0, 16, 9], np.int32)
+    r, c = 11, 9
+    row_out, col_out = np.empty(ncol), np.empty(nrow)
+    block, rowsel, colsel = np.empty(len(rows) * len(cols)), np.empty(len(cols)), np.empty(len(rows))
+    cols_out, rows_out = np.empty(nrow * len(cols)), np.empty(len(rows) * ncol)
+    assert shim.dropin_dense_parts(i, p, x, nrow, ncol, len(x), r, c, rows, len(rows), cols, len(cols), row_out, col_out, block,
+                                   rowsel, colsel, cols_out, rows_out) == 0, shim.dropin_last_error()
+    assert np.array_equal(row_out, dense[r, :]) and np.array_equal(col_out, dense[:, c])
+    assert np.array_equal(rowsel, dense[r, cols]) and np.array_equal(colsel, dense[rows, c])
+    assert np.array_equal(block.reshape(len(cols), len(rows)).T, dense[np.ix_(rows, cols)])
+    assert np.array_equal(cols_out.reshape(len(cols), nrow).T, dense[:, cols])
+    assert np.array_equal(rows_out.reshape(ncol, len(rows)).T, dense[rows, :])
+
+
+@pytest.mark.parametrize("col", [0, 3, 9, 16])
+def test_dropin_range_cursors(shim, col):
+    """InnerIteratorInRange / NotInRange, InnerIndices, emptyInnerIndices (reference :196-216, :238-321)."""
+    dense, i, p, x = _small_matrix(2)
+    nrow, ncol = dense.shape
+    for s in (np.array([], np.uint32), np.arange(nrow, dtype=np.uint32), np.array([0, 2, 5, 6, 7, 11, 19, 22], np.uint32)):
+        in_rows, in_vals, out_rows, out_vals = (np.empty(nrow, np.int32), np.empty(nrow), np.empty(nrow, np.int32), np.empty(nrow))
+        inner, empty = np.empty(nrow, np.uint32), np.empty(nrow, np.uint32)
+        n_in, n_out, n_inner, n_empty = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        s_arg = s if len(s) else np.zeros(1, np.uint32)
+        assert shim.dropin_range_cursors(i, p, x, nrow, ncol, len(x), col, s_arg, len(s), in_rows, in_vals, C.byref(n_in), out_rows,
+                                         out_vals, C.byref(n_out), inner, C.byref(n_inner), empty, C.byref(n_empty)) == 0
+        stored = np.nonzero(dense[:, col])[0]
+        want_in = np.array([r for r in stored if r in set(s.tolist())], np.int64)
+        want_out = np.array([r for r in stored if r not in set(s.tolist())], np.int64)
+        assert in_rows[:n_in.value].tolist() == want_in.tolist() and np.array_equal(in_vals[:n_in.value], dense[want_in, col])
+        assert out_rows[:n_out.value].tolist() == want_out.tolist() and np.array_equal(out_vals[:n_out.value], dense[want_out, col])
+        assert inner[:n_inner.value].tolist() == stored.tolist()
+        assert empty[:n_empty.value].tolist() == [r for r in range(nrow) if dense[r, col] == 0.0]
+
+
+def test_dropin_row_cursor_and_symmetry(shim):
+    """InnerRowIterator walks a row's stored entries in column order; isAppxSymmetric tests A(r,c) == A(c,r)."""
+    dense, i, p, x = _small_matrix(3)
+    nrow, ncol = dense.shape
+    for row in (0, 5, 11, 22):
+        cols, vals, n, sym = np.empty(ncol, np.int32), np.empty(ncol), C.c_int(), C.c_int()
+        assert shim.dropin_row_cursor(i, p, x, nrow, ncol, len(x), row, cols, vals, C.byref(n), C.byref(sym)) == 0
+        want = np.nonzero(dense[row, :])[0]
+        assert cols[:n.value].tolist() == want.tolist() and np.array_equal(vals[:n.value], dense[row, want])
+        assert sym.value == 0  # not square
+    sd, si, sp_, sx = _small_matrix(4, symmetric=True)
+    cols, vals, n, sym = np.empty(sd.shape[1], np.int32), np.empty(sd.shape[1]), C.c_int(), C.c_int()
+    assert shim.dropin_row_cursor(si, sp_, sx, sd.shape[0], sd.shape[1], len(sx), 1, cols, vals, C.byref(n), C.byref(sym)) == 0
+    assert sym.value == 1
+    sx2 = sx.copy()
+    sx2[len(sx2) // 2] += 1.0  # one entry off: no longer symmetric (unless it sits on the diagonal)
+    k = len(sx2) // 2
+    col_of = np.searchsorted(sp_, k, side="right") - 1
+    if si[k] != col_of:
+        assert shim.dropin_row_cursor(si, sp_, sx2, sd.shape[0], sd.shape[1], len(sx2), 1, cols, vals, C.byref(n), C.byref(sym)) == 0
+        assert sym.value == 0
