@@ -1,12 +1,15 @@
 """CPU tests of the oracle itself (no GPU): the C port and, where present, the compiled
 reference must reproduce the committed golden vectors bit for bit; transpose and SpMV —
 for which the reference holds no code — are cross-checked against scipy.sparse."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
 
 from oracle import oracle
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VEC_OPS = ("columnSums", "colSums", "rowSums", "colMeans", "rowMeans")
 
 
@@ -129,3 +132,21 @@ def test_crossprod_known_answer_on_the_vignette_matrix():
     for chk in ([oracle.Port()] + ([oracle.Ref()] if oracle.Ref.available() else [])):
         got = chk.crossprod(i, p, x, 5, 5)
         assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), chk.kind
+
+
+@pytest.mark.parametrize("n_super,chunk", [(1, 1000), (8, 1000), (5, 37), (13, 100000)])
+def test_two_level_transpose_spec_is_the_canonical_transpose(n_super, chunk):
+    """tools/transpose_two_level_spec.py (the plan for tall matrices): a stable partition into
+    row super-bands followed by a stable split inside each is the counting-sort transpose, bit for bit."""
+    import importlib.util
+
+    from rcppsparse_b200 import synth
+
+    spec_ = importlib.util.spec_from_file_location("two_level", os.path.join(ROOT, "tools", "transpose_two_level_spec.py"))
+    mod = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mod)
+    for spec in (synth.powerlaw_spec(3000, 400, 25.0, 5, row_levels=4), synth.uniform_spec(20000, 150, 0.004, 6)):
+        i, p, x = synth.generate_host(spec)
+        ti, tp, tx = mod.transpose_two_level(i, p, x, spec.nrow, spec.ncol, n_super, chunk)
+        ri, rp, rx = oracle.Port().transpose(i, p, x, spec.nrow, spec.ncol)
+        assert np.array_equal(tp, rp) and np.array_equal(ti, ri) and np.array_equal(tx.view(np.uint64), rx.view(np.uint64))
