@@ -12,14 +12,23 @@ rowMeans (reference RcppSparse.h:131-156) — over the device-resident matrix.
 `value` = stored entries swept per second over the whole job = ops * nnz / step time.
 
 At N > 1 (torchrun, one rank per GPU) every rank owns a C2-sized column block of a
-1M x (100k*N) matrix (weak scaling; columns are independent units), column results are
-all-gathered and row results all-reduced over NCCL inside the timed step.
+1M x (100k*N) matrix (weak scaling; columns are independent units); inside the timed step column
+results are assembled and row results summed by the library's exchange kernels over NVLink peer
+memory (--exchange nccl: torch.distributed all-gather / all-reduce instead), each op's exchange running
+beside the next op's sweep, every result waited for before its step ends.
 
-Extra keys beside the base contract: `per_op`, `roofline` (dominant kernel: the rowSums kernel —
-banded shared-memory scatter at C2 — algorithmic bytes 12*nnz + 8*nrow per launch, timed live with
-CUDA events on the launching stream), `cpu_baseline` (reference code on a bounded column block, rank 0, N=1),
-`e2e` (same step through the host-buffer C ABI: upload of i/p/x from pinned memory + four
-results read back, every step), `clocks`, `gpu_launches`.
+Row sums of a RESIDENT mirror: the library serves rowSums/rowMeans with its scatter kernels until a mirror has
+been asked for them more than 8 times, then from a row-ordered copy it builds once (sparse_b200.h).  The
+steady state measured here is the second regime; the first is timed before warm-up and reported in
+`row_companion` (scatter time per call, one-off build time, and `value_before_row_copy`: the same step
+with the row sums still on the scatter kernel).  --no-row-companion keeps the whole run in the first regime.
+
+Extra keys beside the base contract: `per_op`, `roofline` (slowest op's kernel: algorithmic bytes per launch
+from sb200_algorithmic_bytes, timed live with CUDA events on the launching stream, `traffic` from the
+committed ncu capture), `row_path`, `row_companion`, `exchange` (N > 1), `cpu_baseline` (reference code on a
+bounded column block, rank 0, N=1), `e2e` (same step through the host-buffer C ABI: upload of i/p/x from pinned
+memory + four results read back into pinned buffers, every step; `e2e.pageable`: the same from ordinary host
+arrays, what an R caller owns), `clocks`, `gpu_launches`.
 """
 from __future__ import annotations
 
