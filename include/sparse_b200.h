@@ -137,6 +137,20 @@ int sb200_matrix_row_path(sb200_matrix* m, int* banded);
  * -1 = drop and never build. */
 int sb200_matrix_row_companion(sb200_matrix* m, int action);
 
+/* Band-major companion of a RESIDENT mirror, for the two products.  A^T v gathers v[i[k]] once per stored entry; on
+ * the CSC arrays those gathers go to L2 (8 MB of operand does not fit shared memory) and its request rate, not
+ * HBM, bounds the sweep.  A mirror that is asked for A^T v more than SB200_ROW_COMPANION_AFTER times (default 8) and
+ * owns its arrays keeps a copy of its entries regrouped by (row band of <= 12288 rows, column) with 16-bit
+ * in-band row ids (+10 B per entry of HBM, one pass to build): the operand's slice of a band then sits in shared
+ * memory while the band's entries stream through, and a (column, band) run leaves as one FP64 reduction on
+ * y[column].  A v is the same sweep on the row-ordered copy's own companion (which = 1 builds both).  Same
+ * arithmetic every call: only the layout is kept.  sb200_matrix_refresh_values drops it.
+ * which: 0 = the layout A^T v runs on, 1 = the layout A v runs on; action: 1 build now, 0 drop, -1 drop and never build. */
+int sb200_matrix_band_companion(sb200_matrix* m, int which, int action);
+/* Bit mask of the cached layouts this mirror holds: 1 row-ordered copy, 2 band-major companion (A^T v),
+ * 4 band-major companion of the row-ordered copy (A v), 8 transpose plan. */
+int sb200_matrix_layouts(sb200_matrix* m, int* mask);
+
 /* ---- cross-GPU exchange for column-sharded matrices (one process per GPU, GPUs of one node) ---------
  * The reference is single-process; a column-sharded deployment needs two exchange steps:
  * assembling column-indexed results from disjoint slices, and summing full-length row-indexed partials.
@@ -163,6 +177,11 @@ int sb200_exchange_reduce(sb200_exchange* x, void* cuda_stream, int64_t partial_
 int sb200_exchange_barrier(sb200_exchange* x, void* cuda_stream);
 /* Synchronises the device; SB200_E_CUDA if a barrier gave up waiting for a peer (~4 s). */
 int sb200_exchange_status(sb200_exchange* x);
+
+/* Scratch, results and cached layouts come from the device's stream-ordered memory pool, which keeps freed blocks
+ * for reuse (a multi-GB cudaMalloc/cudaFree pair costs as much as a sweep).  sb200_trim synchronises the device and
+ * hands everything the pool holds but does not use back to the driver (e.g. before another library allocates). */
+int sb200_trim(int device);
 
 /* ---- introspection for benchmarks ----------------------------------------------------------
  * Number of kernel launches this library has issued in this process (all handles). */

@@ -216,9 +216,23 @@ class Ref:
         return out
 
 
-def best() -> "Port | Ref":
-    """The strongest checker present: the compiled reference if it is here, else the port."""
-    return Ref() if Ref.available() else Port()
+EXPECT_REF = os.path.join(HERE, "EXPECT_REF")  # tracked marker: this repo's GPU runs are checked against the compiled reference
+
+
+def best(strict: bool | None = None) -> "Port | Ref":
+    """The strongest checker present: the compiled reference if it is here, else the port.
+    strict (default: whether oracle/EXPECT_REF exists and SB200_ORACLE_ALLOW_PORT is unset): raise instead of
+    silently falling back to the port when the compiled reference was expected to travel with the snapshot."""
+    if Ref.available():
+        return Ref()
+    if strict is None:
+        strict = os.path.exists(EXPECT_REF) and not os.environ.get("SB200_ORACLE_ALLOW_PORT")
+    if strict:
+        raise FileNotFoundError(
+            REF_SO + " is missing: the parity checks of this repo run against the reference's own compiled code "
+            "(`make -C oracle ref` where /root/reference exists; oracle/_ref travels with the gpurun snapshot). "
+            "Set SB200_ORACLE_ALLOW_PORT=1 to accept the C port instead.")
+    return Port()
 
 
 # ------------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@ SYMBOLS = [
     "sb200_col_sums_dev", "sb200_row_sums_dev", "sb200_spmv_dev", "sb200_spmv_t_dev", "sb200_transpose_dev",
     "sb200_vec_div_dev", "sb200_launch_count", "sb200_algorithmic_bytes", "sb200_synth_create",
     "sb200_synth_vector_dev", "sb200_matrix_download_columns", "sb200_matrix_row_path", "sb200_matrix_row_companion",
-    "sb200_crossprod", "sb200_crossprod_dev",
+    "sb200_crossprod", "sb200_crossprod_dev", "sb200_matrix_band_companion", "sb200_matrix_layouts", "sb200_trim",
     "sb200_exchange_create", "sb200_exchange_connect", "sb200_exchange_destroy", "sb200_exchange_window",
     "sb200_exchange_gather", "sb200_exchange_reduce", "sb200_exchange_barrier", "sb200_exchange_status",
 ]
@@ -84,6 +84,9 @@ def lib() -> C.CDLL:
         "sb200_matrix_download_columns": ([vp, i64, i64, vp, vp, vp, C.POINTER(i64)], C.c_int),
         "sb200_matrix_row_path": ([vp, C.POINTER(C.c_int)], C.c_int),
         "sb200_matrix_row_companion": ([vp, C.c_int], C.c_int),
+        "sb200_matrix_band_companion": ([vp, C.c_int, C.c_int], C.c_int),
+        "sb200_matrix_layouts": ([vp, C.POINTER(C.c_int)], C.c_int),
+        "sb200_trim": ([C.c_int], C.c_int),
         "sb200_crossprod": ([vp, vp], C.c_int),
         "sb200_crossprod_dev": ([vp, vp], C.c_int),
         "sb200_exchange_create": ([C.c_int, i64, pp, vp], C.c_int),

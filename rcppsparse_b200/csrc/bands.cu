@@ -41,6 +41,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "walk.cuh"
 
 namespace sb200 {
 
@@ -288,45 +289,6 @@ __device__ __forceinline__ int32_t band_start(const BandView& a, int b, int64_t 
   if (b == 0) return __ldg(a.p + c);
   if (b == a.nb) return __ldg(a.p + c + 1);
   return __ldg(a.bpt + static_cast<int64_t>(b - 1) * a.ncol + c);
-}
-
-// One warp, 32 runs (start s, length len per lane).  The concatenated entries are walked 32*U at a
-// time in lane order = (run, position) order: for every group of U steps first load(k, l, valid) is
-// called U times (all loads of the group are in flight together — the kernels are latency-bound
-// otherwise), then use(payload) U times in step order.  k = entry index, l = lane owning the run.
-// Every lane calls load/use in every step (valid = false past the end), so they may use warp-wide
-// primitives.
-template <int U, typename Payload, typename Load, typename Use>
-__device__ __forceinline__ void warp_walk_runs(int32_t s, int32_t len, int lane, Load load, Use use) {
-  int32_t incl = len;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const int32_t up = __shfl_up_sync(0xffffffffu, incl, off);
-    if (lane >= off) incl += up;
-  }
-  const int32_t excl = incl - len;
-  const int32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  for (int32_t base = 0; base < total; base += 32 * U) {
-    Payload pl[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int32_t q = base + u * 32 + lane;
-      int l = 0;  // largest l with excl[l] <= q (skips empty runs)
-#pragma unroll
-      for (int step = 16; step > 0; step >>= 1) {
-        const int cand = l + step;
-        const int32_t e = __shfl_sync(0xffffffffu, excl, cand & 31);
-        if (cand < 32 && e <= q) l = cand;
-      }
-      const int32_t rs = __shfl_sync(0xffffffffu, s, l);
-      const int32_t re = __shfl_sync(0xffffffffu, excl, l);
-      pl[u] = load(rs + (q - re), l, q < total);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (base + u * 32 < total) use(pl[u]);  // warp-uniform
-    }
-  }
 }
 
 // ================================================================================================
@@ -910,17 +872,7 @@ static int build_band_plan(sb200_matrix* m, int rows_cap, int want_bands, int S,
   SB_CUDA(cudaMemcpyAsync(&h_maxrows, d_maxrows, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   tr.mark("bands");
   // ---- P3 ---------------------------------------------------------------------------------------------
-  if (nb > 1) {
-    const size_t smem = sizeof(int32_t) * (2 * (SWEEP_TILE + 4) + static_cast<size_t>(nb) + 1);
-    SB_CUDA(cudaFuncSetAttribute(band_ptr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    int64_t blocks = m->n_tiles;
-    const int64_t capb = static_cast<int64_t>(m->sm_count) * 6;
-    if (blocks > capb) blocks = capb;
-    band_ptr_kernel<<<static_cast<unsigned>(blocks), BP_THREADS, smem, st>>>(m->d_i, m->d_p, m->d_plan, m->n_tiles, ncol,
-                                                                            static_cast<int32_t>(nnz), bp->d_rb, nb, bp->d_bpt);
-    count_launch();
-    SB_CUDA(cudaGetLastError());
-  }
+  SB_TRY(launch_band_ptr(m, bp->d_rb, nb, bp->d_bpt));
   tr.mark("band ptrs");
   SB_CUDA(cudaStreamSynchronize(st));
   bp->max_rows = h_maxrows;
@@ -928,6 +880,24 @@ static int build_band_plan(sb200_matrix* m, int rows_cap, int want_bands, int S,
   if (h_maxrows > rows_cap) return fail(SB200_E_UNSUPPORTED, "band plan: a row band exceeds its shared-memory budget");
   guard.armed = false;
   *out = bp;
+  return SB200_OK;
+}
+
+// Band pointers for caller-given band bounds d_rb[0..nb] (rb[0] = 0, rb[nb] = nrow, non-decreasing), on the
+// matrix's stream: d_bpt[(b-1)*ncol + c] = first k of column c with i[k] >= rb[b], b = 1..nb-1.  Used by the band
+// plan above and by the band-major companion builder (bmc.cu).
+int launch_band_ptr(sb200_matrix* m, const int32_t* d_rb, int nb, int32_t* d_bpt) {
+  if (nb <= 1 || m->n_tiles == 0) return SB200_OK;
+  const size_t smem = sizeof(int32_t) * (2 * (SWEEP_TILE + 4) + static_cast<size_t>(nb) + 1);
+  if (smem > 220 * 1024) return fail(SB200_E_UNSUPPORTED, "band pointers: too many row bands for one pass");
+  SB_CUDA(cudaFuncSetAttribute(band_ptr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int64_t blocks = m->n_tiles;
+  const int64_t capb = static_cast<int64_t>(m->sm_count) * 6;
+  if (blocks > capb) blocks = capb;
+  band_ptr_kernel<<<static_cast<unsigned>(blocks), BP_THREADS, smem, m->stream>>>(m->d_i, m->d_p, m->d_plan, m->n_tiles, m->ncol,
+                                                                                  static_cast<int32_t>(m->nnz), d_rb, nb, d_bpt);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
   return SB200_OK;
 }
 

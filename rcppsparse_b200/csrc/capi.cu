@@ -88,6 +88,7 @@ static void free_matrix(sb200_matrix* m) {
     pool_free(m->d_x, fs);
   }
   free_matrix_plans(m, fs);
+  drop_band_companion(m, fs);
   pool_free(m->d_plan, fs);
   pool_free(m->d_plan_g, fs);
   pool_free(m->d_ws, fs);
@@ -164,6 +165,26 @@ static int enqueue_finish(sb200_matrix* m, unsigned flags) {
   return SB200_OK;
 }
 
+// Free device memory as an allocation from the pool sees it: what the driver reports plus what the pool has
+// reserved but is not using (the release threshold keeps freed blocks in the pool).
+size_t device_free_bytes() {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t reserved = 0, used = 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+      free_b += static_cast<size_t>(reserved - used);
+  }
+  cudaGetLastError();
+  return free_b;
+}
+
 int row_companion_after() {
   static const int after = [] {
     const char* ev = getenv("SB200_ROW_COMPANION_AFTER");
@@ -189,12 +210,8 @@ int build_row_companion(sb200_matrix* m) {
   if (m->rows_state == 1) return SB200_OK;
   m->rows_state = -1;
   if (m->nnz == 0 || m->nrow == 0) return SB200_OK;
-  size_t free_b = 0, total_b = 0;
   const size_t need = 12ull * static_cast<size_t>(m->nnz) + 64ull * static_cast<size_t>(m->nrow);
-  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < 3 * need) {
-    cudaGetLastError();
-    return SB200_OK;
-  }
+  if (device_free_bytes() < 2 * need) return SB200_OK;  // the copy plus the transpose's own scratch
   const std::string saved = t_last_error;
   sb200_matrix* t = nullptr;
   int rc = alloc_matrix(m->device, m->ncol, m->nrow, m->nnz, &t);
@@ -251,6 +268,17 @@ int sb200_device_count(int* count) {
   return SB200_OK;
 }
 
+int sb200_trim(int device) {
+  SB_TRY(require_device(device));
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(SB200_E_CUDA, "cudaSetDevice failed");
+  SB_CUDA(cudaDeviceSynchronize());
+  cudaMemPool_t pool;
+  SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  SB_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return SB200_OK;
+}
+
 int64_t sb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int32_t nrow, int32_t ncol, int64_t nnz,
@@ -288,7 +316,16 @@ int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int
   cudaError_t e = cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking);
   int rc = SB200_OK, rc_x = SB200_OK;
   std::thread x_thread;
-  if (e == cudaSuccess && (stage_i || stage_x)) e = cudaStreamSynchronize(m->stream);  // the arrays exist (allocated in stream order)
+  // i/p/x were allocated in m->stream's order; every other stream or thread that writes them waits for that
+  if (e == cudaSuccess && (stage_i || stage_x)) {
+    e = cudaStreamSynchronize(m->stream);
+  } else if (e == cudaSuccess) {
+    cudaEvent_t allocated = nullptr;
+    e = cudaEventCreateWithFlags(&allocated, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(allocated, m->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(xs, allocated, 0);
+    if (allocated) cudaEventDestroy(allocated);
+  }
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_p, p, bp, cudaMemcpyHostToDevice, m->stream);
   if (e == cudaSuccess && nnz > 0) {
     if (stage_i)
@@ -392,6 +429,7 @@ int sb200_matrix_refresh_values(sb200_matrix* m, const double* x) {
   if (m->nnz == 0) return SB200_OK;
   if (!x) return fail(SB200_E_INVALID, "x is NULL");
   drop_row_companion(m);  // its values are the old ones; the call count starts over
+  drop_band_companion(m, m->stream);
   const size_t bx = sizeof(double) * static_cast<size_t>(m->nnz);
   if (bx >= STAGED_COPY_MIN_BYTES && host_is_pageable(x)) {
     SB_CUDA(cudaStreamSynchronize(m->stream));  // nothing on the stream still reads the old values
@@ -463,6 +501,8 @@ int sb200_transpose_dev(sb200_matrix* m, sb200_matrix** out) {
   // the result is canonical by construction; skip re-validation
   if (rc == SB200_OK) rc = finish_matrix(t, SB200_NO_VALIDATE);
   if (rc != SB200_OK) {
+    cudaStreamSynchronize(m->stream);  // kernels on m's stream may still be writing t's arrays
+    cudaGetLastError();
     free_matrix(t);
     return rc;
   }
@@ -541,6 +581,10 @@ int sb200_transpose(sb200_matrix* m, int32_t* p_out, int32_t* i_out, double* x_o
     if (e == cudaSuccess && stage_i) rc = staged_d2h(m->device, i_out, t->d_i, bi);
     if (e == cudaSuccess && rc == SB200_OK && stage_x) rc = staged_d2h(m->device, x_out, t->d_x, bx);
   }
+  if (rc != SB200_OK || e != cudaSuccess) {
+    cudaStreamSynchronize(m->stream);  // nothing on m's stream still touches t's arrays when they are freed
+    cudaGetLastError();
+  }
   free_matrix(t);
   if (rc != SB200_OK) return rc;
   if (e != cudaSuccess) return cuda_fail(e, "download of the transposed matrix", __FILE__, __LINE__);
@@ -590,12 +634,11 @@ int sb200_crossprod(sb200_matrix* m, double* out) {
   if (m->ncol == 0) return SB200_OK;
   if (!out) return fail(SB200_E_INVALID, "output buffer is NULL");
   const size_t bytes = sizeof(double) * static_cast<size_t>(m->ncol) * static_cast<size_t>(m->ncol);
-  size_t free_b = 0, total_b = 0;
-  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && bytes > free_b / 2)
-    return fail(SB200_E_NOMEM, "crossprod: the dense ncol x ncol result does not fit on the device");
-  cudaGetLastError();
   double* d_res = nullptr;
-  SB_TRY(pool_alloc(reinterpret_cast<void**>(&d_res), bytes, m->stream));
+  if (pool_alloc(reinterpret_cast<void**>(&d_res), bytes, m->stream) != SB200_OK) {
+    cudaGetLastError();
+    return fail(SB200_E_NOMEM, "crossprod: the dense ncol x ncol result does not fit on the device");
+  }
   int rc = crossprod_into(m, d_res);
   if (rc == SB200_OK) {
     cudaError_t e = cudaMemcpyAsync(out, d_res, bytes, cudaMemcpyDeviceToHost, m->stream);
@@ -627,6 +670,45 @@ int sb200_matrix_row_companion(sb200_matrix* m, int action) {
   }
   drop_row_companion(m);
   m->rows_state = action < 0 ? -1 : 0;
+  return SB200_OK;
+}
+
+int sb200_matrix_band_companion(sb200_matrix* m, int which, int action) {
+  ENTER(m);
+  if (which != 0 && which != 1) return fail(SB200_E_INVALID, "which must be 0 (A^T v) or 1 (A v)");
+  sb200_matrix* t = m;
+  if (which == 1) {  // A v runs on the row-ordered copy: that copy's own companion
+    if (action > 0 && m->rows_state != 1) {
+      m->rows_state = 0;
+      SB_TRY(build_row_companion(m));
+    }
+    if (m->rows_state != 1) {
+      if (action > 0 && m->nnz > 0 && m->nrow > 0)
+        return fail(SB200_E_NOMEM, "row companion could not be built (memory, or the transpose does not support this shape)");
+      return SB200_OK;
+    }
+    t = m->rows;
+    t->stream = m->stream;
+  }
+  if (action > 0) {
+    if (t->bmc_state != 1) {
+      t->bmc_state = 0;
+      SB_TRY(build_band_companion(t));
+    }
+    if (t->bmc_state != 1 && t->nnz > 0 && t->nrow > 0 && t->ncol > 0)
+      return fail(SB200_E_NOMEM, "band-major companion could not be built (memory, or too many (band, column) runs)");
+    return SB200_OK;
+  }
+  drop_band_companion(t, m->stream);
+  t->bmc_state = action < 0 ? -1 : 0;
+  return SB200_OK;
+}
+
+int sb200_matrix_layouts(sb200_matrix* m, int* mask) {
+  ENTER(m);
+  if (!mask) return fail(SB200_E_INVALID, "mask is NULL");
+  *mask = (m->rows_state == 1 ? 1 : 0) | (m->bmc_state == 1 ? 2 : 0) |
+          ((m->rows_state == 1 && m->rows && m->rows->bmc_state == 1) ? 4 : 0) | (m->plan_transpose ? 8 : 0);
   return SB200_OK;
 }
 

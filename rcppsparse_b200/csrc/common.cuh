@@ -51,7 +51,8 @@ constexpr int NUM_SMS_B200 = 148;
 // ---------------------------------------------------------------------------------------------
 // the device-resident mirror
 // ---------------------------------------------------------------------------------------------
-struct BandPlan;  // transpose.cu
+struct BandPlan;       // bands.cu
+struct BandCompanion;  // bmc.cu
 
 }  // namespace sb200
 
@@ -92,6 +93,13 @@ struct sb200_matrix {
   sb200_matrix* rows;
   int rows_state;     // 0 not built, 1 built, -1 never (disabled, or the build failed once)
   int row_sum_calls;  // row-indexed calls served by the scatter kernels since the last (re)build decision
+  // Band-major companion for A^T v (bmc.cu): the entries regrouped by (row band, column), local 16-bit row ids, so
+  // that the operand's slice of a band sits in shared memory while the band's entries stream through the TMA ring.
+  // Built after `row_companion_after()` A^T v calls on a mirror that owns its arrays (A v: the same on `rows`).
+  sb200::BandCompanion* bmc;
+  int bmc_state;      // 0 not built, 1 built, -1 never
+  int spmv_t_calls;   // A^T v calls served by the L2-gather sweep since the last (re)build decision
+  sb200::BandPlan* plan_transpose;  // band plan of the transpose, kept between calls (structure only)
 };
 
 namespace sb200 {
@@ -138,6 +146,11 @@ int decide_row_path(sb200_matrix* m);
 int decide_gather_path(sb200_matrix* m);
 int launch_band_gather(sb200_matrix* m, const double* d_v, double* d_out);
 int launch_band_scatter(sb200_matrix* m, const double* d_v, double* d_out);  // d_v null = rowSums
+int launch_band_ptr(sb200_matrix* m, const int32_t* d_rb, int nb, int32_t* d_bpt);
+// bmc.cu
+int build_band_companion(sb200_matrix* m);  // non-fatal: leaves bmc_state = -1 when it cannot be built
+void drop_band_companion(sb200_matrix* m, cudaStream_t s);
+int launch_bandsweep(sb200_matrix* m, const double* d_v, double* d_out);  // y[ncol] = A^T v from the companion
 void free_matrix_plans(sb200_matrix* m, cudaStream_t s);
 // hostcopy.cu: pageable host memory through worker threads with pinned chunks (blocking)
 bool host_is_pageable(const void* p);
@@ -155,5 +168,6 @@ int finish_matrix(sb200_matrix* m, unsigned flags);  // validate + plan + worksp
 size_t padded_bytes(size_t bytes);
 int pool_alloc(void** out, size_t bytes, cudaStream_t s);  // stream-ordered, from a retaining pool
 void pool_free(void* ptr, cudaStream_t s);
+size_t device_free_bytes();  // driver-free plus what the pool holds unused
 
 }  // namespace sb200

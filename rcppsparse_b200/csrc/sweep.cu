@@ -626,6 +626,15 @@ int launch_sweep(sb200_matrix* m, SweepMode mode, const double* d_v, double divi
       return launch_sweep(m->rows, SWEEP_SPMV_T, d_v, 0.0, d_out);
     }
   }
+  if (mode == SWEEP_SPMV_T && m->nnz > 0 && m->nrow > 0 && m->ncol > 0) {
+    // A mirror that keeps being asked for A^T v gets a band-major companion (bmc.cu): the operand's slice of a row
+    // band sits in shared memory while the band's entries stream past, instead of one L2 gather per entry.
+    if (m->bmc_state == 0 && m->owns_arrays) {
+      const int after = row_companion_after();
+      if (after > 0 && ++m->spmv_t_calls > after) build_band_companion(m);
+    }
+    if (m->bmc_state == 1) return launch_bandsweep(m, d_v, d_out);
+  }
   if (mode == SWEEP_SPMV_T && m->nnz > 0) {
     SB_TRY(decide_gather_path(m));
     if (m->gather_path == 1) {

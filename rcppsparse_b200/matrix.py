@@ -135,6 +135,17 @@ class DeviceMatrix:
         """1 build the row-ordered copy now, 0 drop it, -1 drop and never build (sparse_b200.h)."""
         check(_lib.lib().sb200_matrix_row_companion(self._h, int(action)))
 
+    def band_companion(self, which: int = 0, action: int = 1) -> None:
+        """Band-major companion (sparse_b200.h): which 0 = the layout A^T v runs on, 1 = the layout A v runs on
+        (builds the row-ordered copy too); action 1 build now, 0 drop, -1 drop and never build."""
+        check(_lib.lib().sb200_matrix_band_companion(self._h, int(which), int(action)))
+
+    def layouts(self) -> int:
+        """Bit mask: 1 row-ordered copy, 2 band-major companion (A^T v), 4 the copy's companion (A v), 8 transpose plan."""
+        m = C.c_int()
+        check(_lib.lib().sb200_matrix_layouts(self._h, C.byref(m)))
+        return m.value
+
     def refresh_values(self, x) -> None:
         check(_lib.lib().sb200_matrix_refresh_values(self._h, _ptr(x)))
 

@@ -415,6 +415,104 @@ def test_row_companion_golden_edges(golden):
             oracle.assert_within("rowMeans", D.row_means(), g["rowMeans"], *args, tol=TOL)
 
 
+# ---------------------------------------------------------------------------------------------------
+# band-major companion: A^T v / A v with the operand's band slice in shared memory (bmc.cu)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("band_rows", ["default", "4096", "256", "16"])
+@pytest.mark.parametrize("case", sorted(SYNTH_CASES))
+def test_band_companion_products_on_synthetic_shapes(case, band_rows, monkeypatch, checker):
+    """Both products from the band-major layouts against the reference's iterator sweeps, for the default band height
+    (12288 rows) and for small ones (many bands per matrix: band switches inside a CTA, runs cut by tile
+    boundaries, empty runs, runs longer than a lane group's reach)."""
+    spec = SYNTH_CASES[case]()
+    if band_rows != "default":
+        if spec.nrow // int(band_rows) > 20000:
+            pytest.skip("more bands than the band-pointer pass takes")
+        monkeypatch.setenv("SB200_BMC_ROWS", band_rows)
+    i, p, x = synth.generate_host(spec)
+    args = (i, p, x, spec.nrow, spec.ncol)
+    v_row = synth.dense_vector(spec.seed + 7, spec.nrow)
+    v_col = synth.dense_vector(spec.seed + 3, spec.ncol)
+    want_t, want = checker.spmv_t(*args, v_row), checker.spmv(*args, v_col)
+    with DeviceMatrix.from_host(*args) as D:
+        D.band_companion(0, 1)
+        assert D.layouts() & 2
+        for _ in range(2):
+            oracle.assert_within("spmv_t", D.spmv_t(v_row), want_t, *args, v=v_row, tol=TOL)
+        D.band_companion(1, 1)
+        assert D.layouts() & 5 == 5 and D.row_path() == "row-companion"
+        for _ in range(2):
+            oracle.assert_within("spmv", D.spmv(v_col), want, *args, v=v_col, tol=TOL)
+        oracle.assert_within("rowSums", D.row_sums(), checker.rowSums(*args), *args, tol=TOL)
+
+
+@pytest.mark.parametrize("lanes", ["4", "8", "32"])
+@pytest.mark.parametrize("regime", ["const_0_1_2", "const_10", "const_100", "const_938_939_940", "long_then_dust", "sawtooth"])
+def test_band_companion_lane_groups_and_run_lengths(regime, lanes, monkeypatch, checker):
+    """Every lane-group width of the band sweep on every run-length regime (the width is normally picked from
+    the mean run length), with 1 band and with 24 bands of 256 rows."""
+    lengths = LENGTH_REGIMES[regime]
+    nrow = 6000
+    i, p, x = _columns_of_lengths(lengths, nrow, zlib_seed(regime) + 5)
+    args = (i, p, x, nrow, len(lengths))
+    v_row = synth.dense_vector(11, nrow)
+    want = checker.spmv_t(*args, v_row)
+    monkeypatch.setenv("SB200_BS_LANES", lanes)
+    for rows in (None, "256"):
+        if rows:
+            monkeypatch.setenv("SB200_BMC_ROWS", rows)
+        with DeviceMatrix.from_host(*args) as D:
+            D.band_companion(0, 1)
+            oracle.assert_within("spmv_t", D.spmv_t(v_row), want, *args, v=v_row, tol=TOL)
+
+
+def test_band_companion_golden_edges(golden, checker):
+    """Empty rows / columns, NaN and Inf values, zero-dimension shapes: the companion is a no-op or exact."""
+    g = golden
+    args = (g["i"], g["p"], g["x"], g["nrow"], g["ncol"])
+    with DeviceMatrix.from_host(*args) as D:
+        D.band_companion(0, 1)
+        D.band_companion(1, 1)
+        for _ in range(2):
+            oracle.assert_within("spmv", D.spmv(g["v_col"]), g["spmv"], *args, v=g["v_col"], tol=TOL)
+            oracle.assert_within("spmv_t", D.spmv_t(g["v_row"]), g["spmv_t"], *args, v=g["v_row"], tol=TOL)
+
+
+def test_band_companion_lifecycle(checker):
+    """Built on its own after SB200_ROW_COMPANION_AFTER (8) A^T v calls on a mirror that owns its arrays, dropped
+    by refresh_values (the values it holds are stale), never built on its own for adopted arrays."""
+    spec = synth.config("C2", 0.02)
+    i, p, x = synth.generate_host(spec)
+    args = (i, p, x, spec.nrow, spec.ncol)
+    v = synth.dense_vector(4, spec.nrow)
+    with DeviceMatrix.from_host(*args) as D:
+        for k in range(8):
+            oracle.assert_within("spmv_t", D.spmv_t(v), checker.spmv_t(*args, v), *args, v=v, tol=TOL)
+            assert not D.layouts() & 2, k
+        oracle.assert_within("spmv_t", D.spmv_t(v), checker.spmv_t(*args, v), *args, v=v, tol=TOL)  # ninth call builds
+        assert D.layouts() & 2
+        x2 = x * 3.0 - 0.25
+        D.refresh_values(x2)
+        assert not D.layouts() & 2
+        args2 = (i, p, x2, spec.nrow, spec.ncol)
+        oracle.assert_within("spmv_t", D.spmv_t(v), checker.spmv_t(*args2, v), *args2, v=v, tol=TOL)
+        D.band_companion(0, 1)
+        oracle.assert_within("spmv_t", D.spmv_t(v), checker.spmv_t(*args2, v), *args2, v=v, tol=TOL)
+        D.band_companion(0, -1)
+        for _ in range(10):
+            D.spmv_t(v)
+        assert not D.layouts() & 2
+    import torch
+
+    di, dp, dx = (torch.from_numpy(a).cuda() for a in (i, p, x))
+    dv = torch.from_numpy(v).cuda()
+    with DeviceMatrix.adopt(di, dp, dx, spec.nrow, spec.ncol) as A:
+        out = torch.empty(spec.ncol, dtype=torch.float64, device="cuda")
+        for _ in range(12):
+            A.spmv_t_dev(dv, out)
+        assert not A.layouts() & 2  # the caller may rewrite dx behind the mirror
+
+
 CROSSPROD_CASES = {
     "C1_cols600": lambda: synth.config("C1", 0.06),                 # 10k rows x 600 columns, 100 per column
     "powerlaw_rows": lambda: synth.powerlaw_spec(3000, 900, 40.0, 21, row_levels=5),  # popular rows: long row lists

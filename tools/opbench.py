@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--tag", default="")
     ap.add_argument("--companion", type=int, default=0, help="1: build the row-ordered copy first, -1: never build it")
+    ap.add_argument("--bmc", type=int, default=0, help="1: build both band-major companions first, -1: never build them")
     a = ap.parse_args()
     import torch
 
@@ -54,6 +55,17 @@ def main():
     D.set_stream(torch.cuda.current_stream().cuda_stream)
     if a.companion:
         D.row_companion(a.companion)
+    if a.bmc:
+        import time as _t
+        for which in (0, 1):
+            if a.bmc < 0 and which == 1 and a.companion >= 0:
+                continue
+            t0 = _t.perf_counter()
+            D.band_companion(which, a.bmc)
+            torch.cuda.synchronize()
+            if a.bmc > 0:
+                print(json.dumps({"tag": a.tag, "workload": spec.name, "build": f"band_companion({which})",
+                                  "ms": round((_t.perf_counter() - t0) * 1e3, 2)}), flush=True)
     dev = torch.device("cuda", 0)
     out_c = torch.empty(max(D.ncol, 1), dtype=torch.float64, device=dev)
     out_r = torch.empty(max(D.nrow, 1), dtype=torch.float64, device=dev)
