@@ -175,7 +175,9 @@ int sb200_exchange_gather(sb200_exchange* x, void* cuda_stream, int64_t full_off
 int sb200_exchange_reduce(sb200_exchange* x, void* cuda_stream, int64_t partial_offset, int64_t result_offset, int64_t n,
                           double divisor);
 int sb200_exchange_barrier(sb200_exchange* x, void* cuda_stream);
-/* Synchronises the device; SB200_E_CUDA if a barrier gave up waiting for a peer (~4 s). */
+/* Synchronises the device; SB200_E_CUDA if a barrier gave up waiting for a peer.  A barrier that sees no signal
+ * from a peer for SB200_EXCHANGE_TIMEOUT_S seconds (default 600) raises the window's error word and traps its kernel: the
+ * stream and every later CUDA call fail, no result computed from partial data is ever returned. */
 int sb200_exchange_status(sb200_exchange* x);
 
 /* Scratch, results and cached layouts come from the device's stream-ordered memory pool, which keeps freed blocks

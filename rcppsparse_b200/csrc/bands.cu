@@ -42,6 +42,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "walk.cuh"
+#include "bandplan.cuh"
 
 namespace sb200 {
 
@@ -273,24 +274,6 @@ constexpr int BAND_THREADS = 512;
 constexpr int BAND_WARPS = BAND_THREADS / 32;
 constexpr int BAND_CH = BAND_THREADS;  // columns per chunk: 32 per warp, one run descriptor per lane
 
-struct BandView {
-  const int32_t* i;
-  const int32_t* p;
-  const double* x;
-  int32_t ncol;
-  int nb;
-  int S;
-  const int32_t* rb;   // [nb+1]
-  const int32_t* cs;   // [S+1]
-  const int32_t* bpt;  // [(nb-1)*ncol]
-};
-
-__device__ __forceinline__ int32_t band_start(const BandView& a, int b, int64_t c) {
-  if (b == 0) return __ldg(a.p + c);
-  if (b == a.nb) return __ldg(a.p + c + 1);
-  return __ldg(a.bpt + static_cast<int64_t>(b - 1) * a.ncol + c);
-}
-
 // ================================================================================================
 // row-indexed sums: rowSums / rowMeans / A v
 // ================================================================================================
@@ -510,7 +493,6 @@ struct TransposeArgs {
   double* x_out;
   int max_rows;  // R capacity of the shared-memory tables (even)
   int cluster;   // CTAs per thread-block cluster (adjacent bands of one split kept on the same chunk), 1 = none
-  int debug;     // timing experiments only (SB200_TRANSPOSE_DEBUG): 1 = skip the result stores, 2 = skip the value loads
 };
 
 constexpr int TR_CAPW = 384;  // flattened entries of a warp's 32 columns kept in shared memory between the passes
@@ -562,10 +544,8 @@ __global__ void __launch_bounds__(BAND_THREADS) band_transpose_kernel(const Tran
         const int idx = warp * MR + r;
         const uint32_t my = rel[idx];
         const uint32_t pos = rowpos[r] + my + __popc(same & lt_mask);
-        if (!(a.debug & 1)) {
-          a.i_out[pos] = col;
-          a.x_out[pos] = xv;
-        }
+        a.i_out[pos] = col;
+        a.x_out[pos] = xv;
         if ((same >> lane) == 1u) rel[idx] = static_cast<uint16_t>(my + __popc(same));  // highest lane of the group
       }
       __syncwarp();
@@ -671,7 +651,7 @@ __global__ void __launch_bounds__(BAND_THREADS) band_transpose_kernel(const Tran
             if (q < total) {
               rr[t] = flatr[q];
               cc[t] = col0 + flatl[q];
-              xx[t] = (a.debug & 2) ? 1.0 : ptx::ld_stream_f64(bv.x + flatk[q]);
+              xx[t] = ptx::ld_stream_f64(bv.x + flatk[q]);
             }
           }
 #pragma unroll
@@ -699,11 +679,6 @@ __global__ void __launch_bounds__(BAND_THREADS) band_transpose_kernel(const Tran
   }
 }
 
-__global__ void zero_i32_kernel(int32_t* d, int64_t n) {
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride) d[k] = 0;
-}
-
 struct PhaseTrace {  // SB200_TRACE=1: per-phase device time on stderr
   bool on;
   cudaStream_t st;
@@ -725,16 +700,6 @@ struct PhaseTrace {  // SB200_TRACE=1: per-phase device time on stderr
 // ================================================================================================
 // the plan
 // ================================================================================================
-struct BandPlan {
-  int nb = 0, S = 0, max_rows = 0;
-  bool has_offsets = false;
-  int32_t* d_rb = nullptr;
-  int32_t* d_cs = nullptr;
-  int32_t* d_bpt = nullptr;
-  int32_t* d_rowptr = nullptr;  // [nrow+1]
-  int32_t* d_off = nullptr;     // [nrow*S+1] scan over (row, split); == d_rowptr when S == 1
-};
-
 namespace {
 void PhaseTrace::report(const char* title, const BandPlan* bp) {
   if (!on) return;
@@ -762,7 +727,7 @@ void free_band_plan(BandPlan* bp, cudaStream_t s) {
 
 // rows_cap: most rows a band may hold (consumer's shared-memory budget); want_bands: preferred band
 // count; S: column splits.  nnz > 0 and nrow > 0 required.
-static int build_band_plan(sb200_matrix* m, int rows_cap, int want_bands, int S, BandPlan** out) {
+int build_band_plan(sb200_matrix* m, int rows_cap, int want_bands, int S, BandPlan** out) {
   cudaStream_t st = m->stream;
   const int32_t nrow = m->nrow, ncol = m->ncol;
   const int64_t nnz = m->nnz;
@@ -901,7 +866,7 @@ int launch_band_ptr(sb200_matrix* m, const int32_t* d_rb, int nb, int32_t* d_bpt
   return SB200_OK;
 }
 
-static BandView make_view(const sb200_matrix* m, const BandPlan* bp) {
+BandView make_view(const sb200_matrix* m, const BandPlan* bp) {
   BandView v;
   v.i = m->d_i;
   v.p = m->d_p;
@@ -1286,92 +1251,25 @@ int launch_band_gather(sb200_matrix* m, const double* d_v, double* d_out) {
   return SB200_OK;
 }
 
-// ---- transpose -------------------------------------------------------------------------------------------
-constexpr int TRANSPOSE_ROWS_CAP = 2432;  // 72 B of tables per row + 48 KB of flat lists: one CTA per SM at the cap, two when small
-
-int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double* d_x_out) {
+// ---- transpose: the banded two-pass placement kernel (the plan and the entry point live in transpose.cu) ---------
+int launch_transpose_banded(sb200_matrix* m, const BandPlan* bp, int32_t* d_i_out, double* d_x_out) {
   cudaStream_t st = m->stream;
-  const int32_t nrow = m->nrow;
-  const int64_t nnz = m->nnz;
-  if (nnz == 0 || nrow == 0) {
-    int64_t blocks = (static_cast<int64_t>(nrow) + 1 + 255) / 256;
-    if (blocks > 1024) blocks = 1024;
-    zero_i32_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(d_p_out, static_cast<int64_t>(nrow) + 1);
-    count_launch();
-    SB_CUDA(cudaGetLastError());
-    return SB200_OK;
-  }
-  int S = 2, bands = m->sm_count;
-  if (const char* e = getenv("SB200_TRANSPOSE_SPLITS")) {
-    const int v = atoi(e);
-    if (v >= 1 && v <= 64) S = v;
-  }
-  if (const char* e = getenv("SB200_TRANSPOSE_BANDS")) {
-    const int v = atoi(e);
-    if (v >= 1) bands = v;
-  }
-  BandPlan* bp = nullptr;
-  SB_TRY(build_band_plan(m, TRANSPOSE_ROWS_CAP, bands, S, &bp));
-  PhaseTrace tr(st);
-  tr.mark("start");
-  int rc = SB200_OK;
-  cudaError_t e = cudaMemcpyAsync(d_p_out, bp->d_rowptr, sizeof(int32_t) * (static_cast<size_t>(nrow) + 1),
-                                  cudaMemcpyDeviceToDevice, st);
-  if (e != cudaSuccess) rc = cuda_fail(e, "copy of the new column pointers", __FILE__, __LINE__);
-  if (rc == SB200_OK) {
-    TransposeArgs a;
-    a.bv = make_view(m, bp);
-    a.off = bp->d_off;
-    a.i_out = d_i_out;
-    a.x_out = d_x_out;
-    a.max_rows = (bp->max_rows + 1) & ~1;
-    const size_t smem = transpose_smem_bytes(a.max_rows);
-    int ctas = smem <= 100 * 1024 ? 2 : 1;
-    int grid = m->sm_count * ctas;
-    if (grid > bp->nb * bp->S) grid = bp->nb * bp->S;
-    e = cudaFuncSetAttribute(band_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    // measured (profiles/r01): clusters of 1 / 2 / 4 adjacent bands in lockstep: scatter 34.6 / 33.0 / 39.9 ms
-    // at C3 — no gain, so off by default
-    int cluster = 1;
-    if (const char* ev = getenv("SB200_TRANSPOSE_CLUSTER")) cluster = atoi(ev);
-    while (cluster > 1 && (bp->nb % cluster != 0 || grid % cluster != 0)) cluster >>= 1;
-    if (cluster < 1) cluster = 1;
-    a.cluster = cluster;
-    a.debug = 0;
-    if (const char* ev = getenv("SB200_TRANSPOSE_DEBUG")) a.debug = atoi(ev);
-    bool launched = false;
-    if (e == cudaSuccess && cluster > 1) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(BAND_THREADS);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = cluster;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      if (cudaLaunchKernelEx(&cfg, band_transpose_kernel, a) == cudaSuccess) {
-        launched = true;
-        count_launch();
-      } else {
-        cudaGetLastError();  // cluster launch not possible with this footprint: free-running CTAs
-        a.cluster = 1;
-      }
-    }
-    if (e == cudaSuccess && !launched) {
-      band_transpose_kernel<<<grid, BAND_THREADS, smem, st>>>(a);
-      count_launch();
-      e = cudaGetLastError();
-    }
-    if (e != cudaSuccess) rc = cuda_fail(e, "band_transpose_kernel", __FILE__, __LINE__);
-  }
-  tr.mark("scatter");
-  tr.report("transpose", bp);
-  free_band_plan(bp, st);  // stream-ordered: released after the kernel
-  return rc;
+  TransposeArgs a;
+  a.bv = make_view(m, bp);
+  a.off = bp->d_off;
+  a.i_out = d_i_out;
+  a.x_out = d_x_out;
+  a.max_rows = (bp->max_rows + 1) & ~1;
+  const size_t smem = transpose_smem_bytes(a.max_rows);
+  int ctas = smem <= 100 * 1024 ? 2 : 1;
+  int grid = m->sm_count * ctas;
+  if (grid > bp->nb * bp->S) grid = bp->nb * bp->S;
+  SB_CUDA(cudaFuncSetAttribute(band_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  a.cluster = 1;  // clusters of adjacent bands in lockstep were measured (profiles/r01): no gain
+  band_transpose_kernel<<<grid, BAND_THREADS, smem, st>>>(a);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  return SB200_OK;
 }
 
 void free_matrix_plans(sb200_matrix* m, cudaStream_t s) {
@@ -1382,6 +1280,10 @@ void free_matrix_plans(sb200_matrix* m, cudaStream_t s) {
   if (m->plan_gather) {
     free_band_plan(m->plan_gather, s);
     m->plan_gather = nullptr;
+  }
+  if (m->plan_transpose) {
+    free_band_plan(m->plan_transpose, s);
+    m->plan_transpose = nullptr;
   }
 }
 

@@ -16,13 +16,13 @@
 //     per entry instead of 12;
 //   * a CTA keeps v[b*bw ..] (96 KB) in shared memory and streams the band's entries through 1-D bulk copies
 //     (cp.async.bulk, SASS UBLKCP) on mbarriers, exactly like the column sweep; every gather is an LDS;
-//   * a run's products are summed by a group of 4 / 8 / 32 lanes and leave as ONE red.global.add.f64 on
-//     y[c] — 8 bytes per (column, band) at L2, nothing per entry.  No carries: a run cut by a tile boundary
-//     simply sends two reductions.
+//   * a run is cut into interleaved pieces of <= 16 entries, a THREAD sums a piece (~7 instructions per entry)
+//     and sends ONE red.global.add.f64 to y[c] — 8 bytes per piece at L2, nothing per entry.  No carries: a
+//     run cut by a tile boundary simply sends two reductions.
 // The work list is the merge path of (run ends, entries) of every band, cut into tiles of 1024 items, so
 // power-law columns, empty runs and dense columns balance alike.  Four consumer groups of 128 threads per CTA
-// share the operand slice and run their own two-stage rings (eight tiles in flight per SM), synchronising only
-// inside the group.
+// share the operand slice; each has its own two-stage ring driven by its own producer warp (eight tiles in
+// flight or in work per SM) and synchronises only inside the group.
 //
 // The layout is structure + values of the mirror, nothing about any result; it is built after the mirror has
 // been asked for A^T v more than SB200_ROW_COMPANION_AFTER times (or on request, sb200_matrix_band_companion),
@@ -32,6 +32,7 @@
 // moves 10N + 4*nb*n + 8*nb*min(bw, m).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <new>
@@ -46,7 +47,9 @@ namespace sb200 {
 struct BandCompanion {
   int bw = 0;            // rows per band
   int nb = 0;            // bands
-  int lanes = 8;         // lanes per run in the sweep (4, 8 or 32), from the mean run length
+  double mean_run = 0.0; // entries per (band, column) run
+  int tile = 1024;       // merge-path items per tile (the tile plan below is cut for it)
+  int stages = 2;        // ring depth per consumer group in the sweep
   int64_t n_tiles = 0;   // tiles over all bands
   int32_t* d_vp = nullptr;   // [nb*ncol + 1] first entry of every (band, column) run, band-major
   uint16_t* d_ri = nullptr;  // [nnz] row inside the band
@@ -59,19 +62,24 @@ namespace {
 
 constexpr int BS_GROUP = 128;  // threads per consumer group
 constexpr int BS_GROUPS = 4;
-constexpr int BS_THREADS = BS_GROUP * BS_GROUPS;
-constexpr int BS_TILE = 1024;  // merge-path items per tile
-constexpr int BS_STAGES = 2;
-constexpr int BS_MAX_BAND_ROWS = 12288;
-constexpr int BS_LONG_LIST = 16;
+constexpr int BS_CONSUMERS = BS_GROUP * BS_GROUPS;
+constexpr int BS_THREADS = BS_CONSUMERS + 32 * BS_GROUPS;  // + one producer warp per group (its lane 0 drives the ring)
+constexpr int BS_MAX_BAND_ROWS = 12288;  // 96 KB of operand per band
+constexpr int BS_LONG_LIST = 36;         // a tile holds at most TILE / (4 * 8 + 1) runs of more than 4 pieces
+constexpr int BS_AHEAD = 0;  // entries the optional L2 prefetch runs ahead of the bulk copies (SB200_BS_AHEAD)
 
-constexpr int BS_X_ELEMS = BS_TILE + 2;   // +1 align-down slack, +1 round-up
-constexpr int BS_A_ELEMS = BS_TILE + 8;   // nc+1 values, +3 align-down, +3 round-up, +1 spare
-constexpr int BS_R_ELEMS = BS_TILE + 16;  // +7 align-down, +7 round-up
-constexpr size_t BS_X_BYTES = ((BS_X_ELEMS * 8 + 15) / 16) * 16;
-constexpr size_t BS_A_BYTES = ((BS_A_ELEMS * 4 + 15) / 16) * 16;
-constexpr size_t BS_R_BYTES = ((BS_R_ELEMS * 2 + 15) / 16) * 16;
-constexpr size_t BS_STAGE_BYTES = BS_X_BYTES + BS_A_BYTES + BS_R_BYTES;
+// Ring geometry: TILE merge-path items per tile, STAGES tiles per consumer group.  The tile size is part of the
+// companion (its tile plan); both are picked at build time (default 1024 x 2; SB200_BS_CFG=tile,stages for tuning).
+template <int TILE>
+struct BsGeom {
+  static constexpr int X_ELEMS = TILE + 2;   // +1 align-down slack, +1 round-up
+  static constexpr int A_ELEMS = TILE + 8;   // nc+1 values, +3 align-down, +3 round-up, +1 spare
+  static constexpr int R_ELEMS = TILE + 16;  // +7 align-down, +7 round-up
+  static constexpr size_t X_BYTES = ((X_ELEMS * 8 + 15) / 16) * 16;
+  static constexpr size_t A_BYTES = ((A_ELEMS * 4 + 15) / 16) * 16;
+  static constexpr size_t R_BYTES = ((R_ELEMS * 2 + 15) / 16) * 16;
+  static constexpr size_t STAGE_BYTES = X_BYTES + A_BYTES + R_BYTES;
+};
 
 struct BsParams {
   const int32_t* vp;
@@ -84,6 +92,10 @@ struct BsParams {
   int32_t nrow, ncol;
   int nb, bw;
   int64_t n_tiles;
+  int64_t nnz;     // entries in ri / x
+  int64_t n_runs;  // nb * ncol (vp has n_runs + 1 entries)
+  int ahead;       // entries the L2 prefetch runs ahead of the bulk copies (0 = no prefetch)
+  int cap_shift;   // a thread sums at most 1 << cap_shift entries (3 or 4)
 };
 
 struct BsMeta {
@@ -98,42 +110,50 @@ struct BsMeta {
 };
 
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(BS_GROUP) : "memory"); }
-// barrier over the group that also tells every thread whether any of them passed a true predicate
-__device__ __forceinline__ bool group_sync_or(int id, bool pred) {
-  uint32_t r;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.u32 q, %2, 0;\n\t"
-      "bar.red.or.pred p, %1, %3, q;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(r)
-      : "r"(id), "r"(static_cast<uint32_t>(pred ? 1 : 0)), "n"(BS_GROUP)
-      : "memory");
-  return r != 0;
+// L2 prefetch of a byte range (cp.async.bulk.prefetch.L2: no shared memory, no completion to wait for)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// L lanes per run.  Runs longer than LONG_CAP entries are summed by the whole group afterwards.
-template <int L>
+// One tile, one consumer group of 128 threads:
+//   pieces  a run of up to cap / 2 cap / 4 cap entries is cut into 1 / 2 / 4 PIECES that interleave (piece p takes
+//           the run's entries p, p + np, p + 2 np, ...: neighbouring lanes read neighbouring entries); one packed
+//           32-bit descriptor per piece, slots handed out by a warp scan + one shared-memory atomic per warp;
+//           longer runs go to a short list and are summed by all 128 threads together, one reduction per warp;
+//   sums    a THREAD per piece walks its <= cap entries: x from the stage, the row id from the stage, the
+//           operand from the band slice, one FMA — ~7 instructions per entry and nothing per run but the
+//           descriptor and one red.global.add.f64 on y[column].
+// (Round 2's first version summed a run with a group of 4-32 lanes: ~100 instructions per entry at 12 entries per
+// run — shuffles, bounds and loop overhead per run per lane; ncu: 317 M warp instructions for 1e8 entries.)
+template <int TILE, int STAGES>
 __global__ void __launch_bounds__(BS_THREADS, 1) bandsweep_kernel(const BsParams prm) {
-  constexpr int NG = BS_GROUP / L;  // runs a group sums at a time
-  constexpr int LONG_CAP = (32 * L < 256) ? 32 * L : 256;
+  using G = BsGeom<TILE>;
+  constexpr int PIECES = TILE / 2 + TILE / 8 + 8;  // non-empty runs of a tile + the extra pieces of split runs (<= nk / 8)
   extern __shared__ __align__(128) unsigned char bsm[];
-  __shared__ uint64_t full_bar[BS_GROUPS][BS_STAGES];
-  __shared__ BsMeta meta[BS_GROUPS][BS_STAGES];
-  __shared__ int long_cnt[BS_GROUPS][BS_STAGES];
-  __shared__ int long_list[BS_GROUPS][BS_STAGES][BS_LONG_LIST][3];
+  __shared__ uint64_t full_bar[BS_GROUPS][STAGES];   // producer -> group: the stage's bytes have landed
+  __shared__ uint64_t empty_bar[BS_GROUPS][STAGES];  // group -> producer: every thread is done with the stage
+  __shared__ BsMeta meta[BS_GROUPS][STAGES];
+  __shared__ int piece_cnt[BS_GROUPS][2];  // by tile parity
+  __shared__ int long_cnt[BS_GROUPS][2];
+  __shared__ int long_list[BS_GROUPS][2][BS_LONG_LIST][3];  // runs of more than 4 pieces: (first entry, length, run)
 
-  const int tid = threadIdx.x, g = tid / BS_GROUP, tg = tid % BS_GROUP, lane = tid & 31;
-  const int lg = tg / L, gl = tg % L;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = tid >= BS_CONSUMERS;
+  const int g = producer ? warp - BS_CONSUMERS / 32 : tid / BS_GROUP;
+  const int tg = tid % BS_GROUP;
   double* vs = reinterpret_cast<double*>(bsm);
   const size_t vs_bytes = (static_cast<size_t>(prm.bw) * 8 + 15) & ~static_cast<size_t>(15);
-  unsigned char* my_stages = bsm + vs_bytes + static_cast<size_t>(g) * BS_STAGES * BS_STAGE_BYTES;
+  unsigned char* my_stages = bsm + vs_bytes + static_cast<size_t>(g) * STAGES * G::STAGE_BYTES;
+  uint32_t* pieces = reinterpret_cast<uint32_t*>(bsm + vs_bytes + static_cast<size_t>(BS_GROUPS) * STAGES * G::STAGE_BYTES) + g * PIECES;
+  const int cap_shift = prm.cap_shift, cap = 1 << cap_shift;
 
-  if (tg == 0) {
-    for (int s = 0; s < BS_STAGES; ++s) {
-      ptx::mbar_init(&full_bar[g][s], 1);
-      long_cnt[g][s] = 0;
+  if (tid < BS_GROUPS) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[tid][s], 1);
+      ptx::mbar_init(&empty_bar[tid][s], 1);
     }
+    piece_cnt[tid][0] = piece_cnt[tid][1] = 0;
+    long_cnt[tid][0] = long_cnt[tid][1] = 0;
     ptx::fence_mbar_init();
   }
   __syncthreads();
@@ -153,7 +173,7 @@ __global__ void __launch_bounds__(BS_THREADS, 1) bandsweep_kernel(const BsParams
     }
     b = lo;
   }
-  uint32_t n_used = 0;  // tiles this group has consumed: stage = n_used % STAGES, parity = (n_used / STAGES) & 1
+  uint32_t n_used = 0;  // tiles this group has been through: stage = n_used % STAGES, parity = (n_used / STAGES) & 1
   int64_t t = t_begin;
   while (t < t_end) {
     while (b + 1 < prm.nb && __ldg(prm.ts + b + 1) <= t) ++b;
@@ -176,112 +196,165 @@ __global__ void __launch_bounds__(BS_THREADS, 1) bandsweep_kernel(const BsParams
     const int64_t first = t + g;
     const int n_my = first < t_hi ? static_cast<int>((t_hi - first + BS_GROUPS - 1) / BS_GROUPS) : 0;
 
-    auto issue = [&](int idx, uint32_t seq) {
-      const int s = static_cast<int>(seq % BS_STAGES);
-      const int64_t j = first + static_cast<int64_t>(idx) * BS_GROUPS - ts_b;  // tile inside the band
-      const int64_t pidx = ts_b + b + j;
-      const int32_t c0 = __ldg(prm.plan + pidx), c1 = __ldg(prm.plan + pidx + 1);
-      const int64_t d0 = j * BS_TILE;
-      int64_t d1 = d0 + BS_TILE;
-      if (d1 > items_b) d1 = items_b;
-      const int32_t k0 = Eb + static_cast<int32_t>(d0 - c0), k1 = Eb + static_cast<int32_t>(d1 - c1);
-      BsMeta mt;
-      mt.c0 = c0;
-      mt.nc = c1 - c0;
-      mt.k0 = k0;
-      mt.nk = k1 - k0;
-      // run-end window: vp[gbase + c0 + 1 .. gbase + min(c1 + 1, ncol)]
-      const int64_t a_first = gbase + c0 + 1;
-      const int64_t a_last = gbase + ((c1 + 1 <= prm.ncol) ? c1 + 1 : prm.ncol);
-      const int64_t a_al = a_first & ~static_cast<int64_t>(3);
-      const int32_t a_cnt = (a_last >= a_first) ? static_cast<int32_t>(((a_last - a_al + 1) + 3) & ~static_cast<int64_t>(3)) : 0;
-      mt.a_off = static_cast<int32_t>(a_first - a_al);
-      const int32_t x_al = k0 & ~1;
-      const int32_t x_cnt = (mt.nk > 0) ? (((k1 - x_al) + 1) & ~1) : 0;
-      mt.x_off = k0 - x_al;
-      const int32_t r_al = k0 & ~7;
-      const int32_t r_cnt = (mt.nk > 0) ? (((k1 - r_al) + 7) & ~7) : 0;
-      mt.r_off = k0 - r_al;
-      mt.pad = 0;
-      meta[g][s] = mt;
-      unsigned char* st = my_stages + static_cast<size_t>(s) * BS_STAGE_BYTES;
-      const uint32_t bytes = static_cast<uint32_t>(a_cnt) * 4u + static_cast<uint32_t>(x_cnt) * 8u + static_cast<uint32_t>(r_cnt) * 2u;
-      ptx::mbar_arrive_expect_tx(&full_bar[g][s], bytes);
-      if (x_cnt > 0) ptx::bulk_g2s(st, prm.x + x_al, static_cast<uint32_t>(x_cnt) * 8u, &full_bar[g][s]);
-      if (a_cnt > 0) ptx::bulk_g2s(st + BS_X_BYTES, prm.vp + a_al, static_cast<uint32_t>(a_cnt) * 4u, &full_bar[g][s]);
-      if (r_cnt > 0) ptx::bulk_g2s(st + BS_X_BYTES + BS_A_BYTES, prm.ri + r_al, static_cast<uint32_t>(r_cnt) * 2u, &full_bar[g][s]);
-    };
-
-    if (tg == 0) {
-      for (int q = 0; q < BS_STAGES && q < n_my; ++q) issue(q, n_used + q);
-    }
-    __syncwarp();
-
-    for (int idx = 0; idx < n_my; ++idx) {
-      const uint32_t seq = n_used + idx;
-      const int s = static_cast<int>(seq % BS_STAGES);
-      ptx::mbar_wait(&full_bar[g][s], (seq / BS_STAGES) & 1u);
-      const BsMeta mt = meta[g][s];
-      const unsigned char* st = my_stages + static_cast<size_t>(s) * BS_STAGE_BYTES;
-      const double* __restrict__ xs = reinterpret_cast<const double*>(st) + mt.x_off;
-      const int32_t* __restrict__ as = reinterpret_cast<const int32_t*>(st + BS_X_BYTES) + mt.a_off;
-      const uint16_t* __restrict__ rs = reinterpret_cast<const uint16_t*>(st + BS_X_BYTES + BS_A_BYTES) + mt.r_off;
-      double* __restrict__ yb = prm.y + mt.c0;
-      const int nseg = mt.nc + 1;  // runs c0 .. c0+nc-1 end in the tile, the last one stays open (may be empty)
-      bool saw_long = false;
-      for (int base = 0; base < nseg; base += NG) {  // trip count uniform over the group
-        const int seg = base + lg;
-        int beg = 0, end = 0;
-        if (seg < nseg) {
-          beg = (seg == 0) ? 0 : as[seg - 1] - mt.k0;
-          end = (seg == mt.nc) ? mt.nk : as[seg] - mt.k0;
+    if (producer) {
+      // ===================== producer warp of group g: lane 0 runs the group's ring ==========================
+      if (lane == 0) {
+        int64_t pidx = ts_b + b + (first - ts_b);  // plan entry of the tile being issued; += GROUPS per tile
+        int32_t c0 = 0, c1 = 0;
+        if (n_my > 0) {
+          c0 = __ldg(prm.plan + pidx);
+          c1 = __ldg(prm.plan + pidx + 1);
         }
-        const int len = end - beg;
-        const bool is_long = len > LONG_CAP;
-        if (is_long) {
-          if (gl == 0) {
-            const int slot = atomicAdd(&long_cnt[g][s], 1);
-            if (slot < BS_LONG_LIST) {
-              long_list[g][s][slot][0] = beg;
-              long_list[g][s][slot][1] = end;
-              long_list[g][s][slot][2] = seg;
-            }
+        for (int idx = 0; idx < n_my; ++idx) {
+          const uint32_t seq = n_used + idx;
+          const int s = static_cast<int>(seq % STAGES);
+          // next tile's plan entries: in flight while this tile is issued (and while the stage is waited for)
+          int32_t nc0 = 0, nc1 = 0;
+          if (idx + 1 < n_my) {
+            nc0 = __ldg(prm.plan + pidx + BS_GROUPS);
+            nc1 = __ldg(prm.plan + pidx + BS_GROUPS + 1);
           }
-          saw_long = true;
-          end = beg;
+          const int64_t j = first + static_cast<int64_t>(idx) * BS_GROUPS - ts_b;  // tile inside the band
+          const int64_t d0 = j * TILE;
+          int64_t d1 = d0 + TILE;
+          if (d1 > items_b) d1 = items_b;
+          const int32_t k0 = Eb + static_cast<int32_t>(d0 - c0), k1 = Eb + static_cast<int32_t>(d1 - c1);
+          BsMeta mt;
+          mt.c0 = c0;
+          mt.nc = c1 - c0;
+          mt.k0 = k0;
+          mt.nk = k1 - k0;
+          // run-end window: vp[gbase + c0 + 1 .. gbase + min(c1 + 1, ncol)]
+          const int64_t a_first = gbase + c0 + 1;
+          const int64_t a_last = gbase + ((c1 + 1 <= prm.ncol) ? c1 + 1 : prm.ncol);
+          const int64_t a_al = a_first & ~static_cast<int64_t>(3);
+          const int32_t a_cnt = (a_last >= a_first) ? static_cast<int32_t>(((a_last - a_al + 1) + 3) & ~static_cast<int64_t>(3)) : 0;
+          mt.a_off = static_cast<int32_t>(a_first - a_al);
+          const int32_t x_al = k0 & ~1;
+          const int32_t x_cnt = (mt.nk > 0) ? (((k1 - x_al) + 1) & ~1) : 0;
+          mt.x_off = k0 - x_al;
+          const int32_t r_al = k0 & ~7;
+          const int32_t r_cnt = (mt.nk > 0) ? (((k1 - r_al) + 7) & ~7) : 0;
+          mt.r_off = k0 - r_al;
+          mt.pad = 0;
+          if (seq >= STAGES) {  // the stage is still being read: wait without stealing the consumers' issue slots
+            while (!ptx::mbar_try_wait(&empty_bar[g][s], ((seq / STAGES) - 1u) & 1u)) __nanosleep(128);
+          }
+          meta[g][s] = mt;
+          unsigned char* st = my_stages + static_cast<size_t>(s) * G::STAGE_BYTES;
+          const uint32_t bytes = static_cast<uint32_t>(a_cnt) * 4u + static_cast<uint32_t>(x_cnt) * 8u + static_cast<uint32_t>(r_cnt) * 2u;
+          ptx::mbar_arrive_expect_tx(&full_bar[g][s], bytes);
+          if (x_cnt > 0) ptx::bulk_g2s(st, prm.x + x_al, static_cast<uint32_t>(x_cnt) * 8u, &full_bar[g][s]);
+          if (a_cnt > 0) ptx::bulk_g2s(st + G::X_BYTES, prm.vp + a_al, static_cast<uint32_t>(a_cnt) * 4u, &full_bar[g][s]);
+          if (r_cnt > 0) ptx::bulk_g2s(st + G::X_BYTES + G::A_BYTES, prm.ri + r_al, static_cast<uint32_t>(r_cnt) * 2u, &full_bar[g][s]);
+          if (prm.ahead > 0) {
+            // optional: pull the stretch `ahead` entries past this tile from HBM into L2 (the band's entries and
+            // run ends are linear streams; the four producers cover them between them)
+            int64_t pk0 = (static_cast<int64_t>(k1) + prm.ahead) & ~static_cast<int64_t>(7);
+            int64_t pk1 = (pk0 + mt.nk + (mt.nk >> 2) + 15) & ~static_cast<int64_t>(7);
+            if (pk1 > prm.nnz) pk1 = prm.nnz & ~static_cast<int64_t>(7);
+            if (pk1 > pk0) {
+              prefetch_l2_bulk(prm.x + pk0, static_cast<uint32_t>(pk1 - pk0) * 8u);
+              prefetch_l2_bulk(prm.ri + pk0, static_cast<uint32_t>(pk1 - pk0) * 2u);
+            }
+            const int64_t ahead_runs = (mt.nk > 0) ? (static_cast<int64_t>(prm.ahead) * (mt.nc + 1)) / mt.nk : static_cast<int64_t>(prm.ahead);
+            int64_t pa0 = (a_last + ahead_runs) & ~static_cast<int64_t>(3);
+            int64_t pa1 = (pa0 + mt.nc + (mt.nc >> 2) + 11) & ~static_cast<int64_t>(3);
+            if (pa1 > prm.n_runs) pa1 = prm.n_runs & ~static_cast<int64_t>(3);
+            if (pa1 > pa0) prefetch_l2_bulk(prm.vp + pa0, static_cast<uint32_t>(pa1 - pa0) * 4u);
+          }
+          c0 = nc0;
+          c1 = nc1;
+          pidx += BS_GROUPS;
         }
-        double a0 = 0.0, a1 = 0.0;
-        int k = beg + gl;
-        for (; k + L < end; k += 2 * L) {
-          a0 = __fma_rn(xs[k], vs[rs[k]], a0);
-          a1 = __fma_rn(xs[k + L], vs[rs[k + L]], a1);
-        }
-        if (k < end) a0 = __fma_rn(xs[k], vs[rs[k]], a0);
-        double acc = __dadd_rn(a0, a1);
-#pragma unroll
-        for (int off = L / 2; off > 0; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
-        if (gl == 0 && len > 0 && !is_long) ptx::red_add_f64(yb + seg, acc);
       }
-      if (group_sync_or(1 + g, saw_long)) {
-        // rare: runs longer than LONG_CAP — all 128 threads on one run, one reduction per warp
-        int nl = long_cnt[g][s];
-        if (nl > BS_LONG_LIST) nl = BS_LONG_LIST;  // cannot happen: a tile holds at most TILE / LONG_CAP such runs
+      __syncwarp();
+    } else {
+      // ======================================= consumer group g ==============================================
+      for (int idx = 0; idx < n_my; ++idx) {
+        const uint32_t seq = n_used + idx;
+        const int s = static_cast<int>(seq % STAGES);
+        const int par = static_cast<int>(seq & 1u);
+        ptx::mbar_wait(&full_bar[g][s], (seq / STAGES) & 1u);
+        const BsMeta mt = meta[g][s];
+        const unsigned char* st = my_stages + static_cast<size_t>(s) * G::STAGE_BYTES;
+        const double* __restrict__ xs = reinterpret_cast<const double*>(st) + mt.x_off;
+        const int32_t* __restrict__ as = reinterpret_cast<const int32_t*>(st + G::X_BYTES) + mt.a_off;
+        const uint16_t* __restrict__ rs = reinterpret_cast<const uint16_t*>(st + G::X_BYTES + G::A_BYTES) + mt.r_off;
+        double* __restrict__ yb = prm.y + mt.c0;
+        const int nseg = mt.nc + 1;  // runs c0 .. c0+nc-1 end in the tile, the last one stays open (may be empty)
+        // ---- pieces --------------------------------------------------------------------------------------
+        // np = 1, 2 or 4 pieces per run (a power of two: no division); longer runs go to the long list
+        for (int base = 0; base < nseg; base += BS_GROUP) {  // trip count uniform over the group
+          const int seg = base + tg;
+          int beg = 0, len = 0;
+          if (seg < nseg) {
+            beg = (seg == 0) ? 0 : as[seg - 1] - mt.k0;
+            len = ((seg == mt.nc) ? mt.nk : as[seg] - mt.k0) - beg;
+          }
+          const bool is_long = len > (cap << 2);
+          const int lg = (len > (cap << 1)) ? 2 : ((len > cap) ? 1 : 0);
+          const int np = (len <= 0 || is_long) ? 0 : (1 << lg);
+          if (is_long) {
+            const int slot = atomicAdd(&long_cnt[g][par], 1);
+            long_list[g][par][slot][0] = beg;
+            long_list[g][par][slot][1] = len;
+            long_list[g][par][slot][2] = seg;
+          }
+          int incl = np;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += up;
+          }
+          int slot0 = 0;
+          if (lane == 31 && incl > 0) slot0 = atomicAdd(&piece_cnt[g][par], incl);
+          slot0 = __shfl_sync(0xffffffffu, slot0, 31);
+          uint32_t* dst = pieces + slot0 + incl - np;
+          const uint32_t common = (static_cast<uint32_t>(lg) << 10) | (static_cast<uint32_t>(seg) << 21);
+          for (int p = 0; p < np; ++p)
+            dst[p] = static_cast<uint32_t>(beg + p) | common | (static_cast<uint32_t>((len - 1 - p) >> lg) << 17);  // count - 1
+        }
+        group_sync(1 + g);
+        // ---- sums: a thread per piece -------------------------------------------------------------------------
+        const int P = piece_cnt[g][par];
+        for (int w = tg; w < P; w += BS_GROUP) {
+          const uint32_t d = pieces[w];
+          int k = static_cast<int>(d & 1023u);
+          const int np = 1 << ((d >> 10) & 7u);
+          int cnt = static_cast<int>((d >> 17) & 15u) + 1;
+          const int seg = static_cast<int>(d >> 21);
+          double a0 = 0.0, a1 = 0.0;
+          for (; cnt >= 2; cnt -= 2, k += 2 * np) {
+            a0 = __fma_rn(xs[k], vs[rs[k]], a0);
+            a1 = __fma_rn(xs[k + np], vs[rs[k + np]], a1);
+          }
+          if (cnt) a0 = __fma_rn(xs[k], vs[rs[k]], a0);
+          ptx::red_add_f64(yb + seg, __dadd_rn(a0, a1));
+        }
+        // ---- long runs (more than 4 pieces): all 128 threads on one run, one reduction per warp ---------------
+        const int nl = long_cnt[g][par];
         for (int q = 0; q < nl; ++q) {
-          const int beg = long_list[g][s][q][0], end = long_list[g][s][q][1], seg = long_list[g][s][q][2];
-          double a0 = 0.0;
-          for (int k = beg + tg; k < end; k += BS_GROUP) a0 = __fma_rn(xs[k], vs[rs[k]], a0);
+          const int beg = long_list[g][par][q][0], end = beg + long_list[g][par][q][1], seg = long_list[g][par][q][2];
+          double a0 = 0.0, a1 = 0.0;
+          int k = beg + tg;
+          for (; k + BS_GROUP < end; k += 2 * BS_GROUP) {
+            a0 = __fma_rn(xs[k], vs[rs[k]], a0);
+            a1 = __fma_rn(xs[k + BS_GROUP], vs[rs[k + BS_GROUP]], a1);
+          }
+          if (k < end) a0 = __fma_rn(xs[k], vs[rs[k]], a0);
+          a0 = __dadd_rn(a0, a1);
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1) a0 = __dadd_rn(a0, __shfl_xor_sync(0xffffffffu, a0, off));
           if (lane == 0) ptx::red_add_f64(yb + seg, a0);
         }
-        group_sync(1 + g);
+        group_sync(1 + g);  // every thread of the group is past its last read of stage s and of the piece list
+        if (tg == 0) {
+          piece_cnt[g][par] = 0;
+          long_cnt[g][par] = 0;
+          ptx::mbar_arrive(&empty_bar[g][s]);
+        }
       }
-      // every thread of the group is past its last read of stage s: refill it
-      if (tg == 0) {
-        long_cnt[g][s] = 0;
-        if (idx + BS_STAGES < n_my) issue(idx + BS_STAGES, seq + BS_STAGES);
-      }
-      __syncwarp();
     }
     n_used += static_cast<uint32_t>(n_my);
     t = t_hi;
@@ -371,11 +444,11 @@ __global__ void __launch_bounds__(256) bmc_copy_kernel(const int32_t* __restrict
 }
 
 // tiles per band, then their running sum (one block; nb is small)
-__global__ void bmc_tiles_kernel(const int32_t* __restrict__ vp, int32_t ncol, int nb, int64_t* __restrict__ ts) {
+__global__ void bmc_tiles_kernel(const int32_t* __restrict__ vp, int32_t ncol, int nb, int tile, int64_t* __restrict__ ts) {
   for (int b = threadIdx.x; b < nb; b += blockDim.x) {
     const int64_t gb = static_cast<int64_t>(b) * ncol;
     const int64_t items = static_cast<int64_t>(__ldg(vp + gb + ncol) - __ldg(vp + gb)) + ncol;
-    ts[b + 1] = (items + BS_TILE - 1) / BS_TILE;
+    ts[b + 1] = (items + tile - 1) / tile;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -390,7 +463,7 @@ __global__ void bmc_tiles_kernel(const int32_t* __restrict__ vp, int32_t ncol, i
 
 // plan[ts[b] + b + j] = run ends of band b before diagonal j*TILE of its merge path (ends win ties), j = 0..T_b
 __global__ void bmc_plan_kernel(const int32_t* __restrict__ vp, const int64_t* __restrict__ ts, int nb, int32_t ncol,
-                                int64_t n_plan, int32_t* __restrict__ plan) {
+                                int tile, int64_t n_plan, int32_t* __restrict__ plan) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= n_plan) return;
   int lo_b = 0, hi_b = nb - 1;  // largest b with ts[b] + b <= idx
@@ -406,7 +479,7 @@ __global__ void bmc_plan_kernel(const int32_t* __restrict__ vp, const int64_t* _
   const int64_t gb = static_cast<int64_t>(b) * ncol;
   const int32_t Eb = vp[gb];
   const int64_t Nb = static_cast<int64_t>(vp[gb + ncol]) - Eb;
-  int64_t d = j * BS_TILE;
+  int64_t d = j * tile;
   if (d > Nb + ncol) d = Nb + ncol;
   int64_t lo = d > Nb ? d - Nb : 0;
   int64_t hi = d < ncol ? d : ncol;
@@ -452,7 +525,14 @@ int build_companion(sb200_matrix* m, BandCompanion** out) {
   bc->bw = bw;
   bc->nb = nb;
   const double mean_run = static_cast<double>(nnz) / static_cast<double>(G > 0 ? G : 1);
-  bc->lanes = mean_run <= 12.0 ? 4 : (mean_run <= 96.0 ? 8 : 32);
+  bc->mean_run = mean_run;
+  if (const char* e = getenv("SB200_BS_CFG")) {  // tuning: tile,stages out of the instantiated set
+    int tl = 0, sg = 0;
+    if (sscanf(e, "%d,%d", &tl, &sg) == 2 && ((tl == 1024 && sg == 2) || (tl == 640 && sg == 3) || (tl == 512 && sg == 4))) {
+      bc->tile = tl;
+      bc->stages = sg;
+    }
+  }
   int32_t* d_rb = nullptr;
   int32_t* d_bpt = nullptr;
   uint32_t* d_cnt = nullptr;
@@ -512,7 +592,7 @@ int build_companion(sb200_matrix* m, BandCompanion** out) {
     count_launch();
     SB_CUDA(cudaGetLastError());
   }
-  bmc_tiles_kernel<<<1, 256, 0, st>>>(bc->d_vp, ncol, nb, bc->d_ts);
+  bmc_tiles_kernel<<<1, 256, 0, st>>>(bc->d_vp, ncol, nb, bc->tile, bc->d_ts);
   count_launch();
   SB_CUDA(cudaGetLastError());
   int64_t n_tiles = 0;
@@ -521,7 +601,7 @@ int build_companion(sb200_matrix* m, BandCompanion** out) {
   bc->n_tiles = n_tiles;
   const int64_t n_plan = n_tiles + nb;
   SB_TRY(pool_alloc(reinterpret_cast<void**>(&bc->d_plan), sizeof(int32_t) * static_cast<size_t>(n_plan + 2), st));
-  bmc_plan_kernel<<<static_cast<unsigned>((n_plan + 255) / 256), 256, 0, st>>>(bc->d_vp, bc->d_ts, nb, ncol, n_plan, bc->d_plan);
+  bmc_plan_kernel<<<static_cast<unsigned>((n_plan + 255) / 256), 256, 0, st>>>(bc->d_vp, bc->d_ts, nb, ncol, bc->tile, n_plan, bc->d_plan);
   count_launch();
   SB_CUDA(cudaGetLastError());
   SB_CUDA(cudaStreamSynchronize(st));
@@ -530,9 +610,12 @@ int build_companion(sb200_matrix* m, BandCompanion** out) {
   return SB200_OK;
 }
 
-template <int L>
-int launch_bandsweep_t(const sb200_matrix* m, const BsParams& prm, size_t smem) {
-  auto kern = bandsweep_kernel<L>;
+template <int TILE, int STAGES>
+int launch_bandsweep_t(const sb200_matrix* m, const BsParams& prm) {
+  constexpr int PIECES = TILE / 2 + TILE / 8 + 8;
+  const size_t smem = ((static_cast<size_t>(prm.bw) * 8 + 15) & ~static_cast<size_t>(15)) + BS_GROUPS * STAGES * BsGeom<TILE>::STAGE_BYTES +
+                      BS_GROUPS * PIECES * sizeof(uint32_t);
+  auto kern = bandsweep_kernel<TILE, STAGES>;
   SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int64_t grid = m->sm_count;
   if (grid > prm.n_tiles) grid = prm.n_tiles;
@@ -590,17 +673,24 @@ int launch_bandsweep(sb200_matrix* m, const double* d_v, double* d_out) {
   prm.nb = bc->nb;
   prm.bw = bc->bw;
   prm.n_tiles = bc->n_tiles;
-  const size_t smem = ((static_cast<size_t>(bc->bw) * 8 + 15) & ~static_cast<size_t>(15)) + BS_GROUPS * BS_STAGES * BS_STAGE_BYTES;
-  int lanes = bc->lanes;
-  if (const char* e = getenv("SB200_BS_LANES")) {
+  prm.nnz = m->nnz;
+  prm.n_runs = static_cast<int64_t>(bc->nb) * m->ncol;
+  prm.ahead = BS_AHEAD;
+  if (const char* e = getenv("SB200_BS_AHEAD")) {
     const int v = atoi(e);
-    if (v == 4 || v == 8 || v == 32) lanes = v;
+    if (v >= 0 && v <= (1 << 22)) prm.ahead = v;
   }
-  switch (lanes) {
-    case 4: return launch_bandsweep_t<4>(m, prm, smem);
-    case 32: return launch_bandsweep_t<32>(m, prm, smem);
-    default: return launch_bandsweep_t<8>(m, prm, smem);
+  // entries per thread: 16 when runs are short (one piece per run, half as many reductions), 8 when they are
+  // long (a 1024-entry tile then cuts into ~128 pieces: one per thread)
+  prm.cap_shift = bc->mean_run >= 48.0 ? 3 : 4;
+  if (const char* e = getenv("SB200_BS_CAP")) {
+    const int v = atoi(e);
+    if (v == 8) prm.cap_shift = 3;
+    if (v == 16) prm.cap_shift = 4;
   }
+  if (bc->tile == 640 && bc->stages == 3) return launch_bandsweep_t<640, 3>(m, prm);
+  if (bc->tile == 512 && bc->stages == 4) return launch_bandsweep_t<512, 4>(m, prm);
+  return launch_bandsweep_t<1024, 2>(m, prm);
 }
 
 }  // namespace sb200

@@ -13,8 +13,10 @@
 // The barrier is an epoch counter per peer in each window: rank r stores epoch e into slot r of every peer
 // (st.release.sys after a system fence), then waits until all of its own slots have reached e
 // (ld.acquire.sys).  Epochs only grow, every rank issues the same sequence of barriers (SPMD), so no slot is
-// ever reset.  A wait gives up after ~4 s and raises the window's error word instead of hanging the GPU.
+// ever reset.  A wait that sees no signal for 10 minutes (SB200_EXCHANGE_TIMEOUT_S) raises the window's error word and TRAPS:
+// the stream fails loudly; it never goes on with data that has not arrived.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -56,33 +58,47 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 // header words of a window (uint32 index): [0,16) epoch slots, 16 error word, 32 CTA counter, 33 go word
 constexpr int XG_W_ERROR = 16, XG_W_COUNT = 32, XG_W_GO = 33;
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// A peer that never signals (its process died, or it skipped a collective call) must not let this rank go on with
+// data that has not arrived: the wait has no early exit.  After `timeout_ns` (default 10 minutes,
+// SB200_EXCHANGE_TIMEOUT_S; legitimate skew between ranks — one rank's host busy with I/O, a checker, a debugger —
+// is seconds) the window's error word is raised and the kernel TRAPS: the stream and every later CUDA call of
+// this process fail loudly instead of returning sums of partial data.
+__device__ __forceinline__ void xg_give_up(const XgPeers& peers, int rank, uint32_t code) {
+  reinterpret_cast<volatile uint32_t*>(peers.base[rank])[XG_W_ERROR] = code;
+  __threadfence_system();
+  __trap();
+}
+
 // Signal epoch to every peer and wait for every peer's signal; called by threads q < world of ONE CTA.
 // Everything this rank's earlier work wrote (locally or into peers) is ordered before the signal by the system
 // fence; everything after the wait sees what the peers wrote before their signals.
-__device__ __forceinline__ void xg_signal_and_wait(const XgPeers& peers, int rank, int q, uint32_t epoch) {
+__device__ __forceinline__ void xg_signal_and_wait(const XgPeers& peers, int rank, int q, uint32_t epoch,
+                                                   unsigned long long timeout_ns) {
   __threadfence_system();
   st_release_sys(reinterpret_cast<uint32_t*>(peers.base[q]) + rank, epoch);
   const uint32_t* mine = reinterpret_cast<const uint32_t*>(peers.base[rank]) + q;
-  // once a wait has given up, later barriers do not wait again (a dead peer must not cost 4 s per call);
-  // sb200_exchange_status reports the failure
-  if (*reinterpret_cast<volatile uint32_t*>(peers.base[rank] + 4 * XG_W_ERROR) != 0u) return;
-  const long long t0 = clock64();
+  const unsigned long long t0 = global_ns();
+  unsigned spins = 0;
   while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) {
-    if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz: a peer is gone
-      reinterpret_cast<uint32_t*>(peers.base[rank])[XG_W_ERROR] = 0x80000000u | static_cast<uint32_t>(q);
-      break;
-    }
+    if ((++spins & 1023u) == 0u && global_ns() - t0 > timeout_ns) xg_give_up(peers, rank, 0x80000000u | static_cast<uint32_t>(q));
     __nanosleep(64);
   }
 }
 
-__global__ void xg_barrier_kernel(XgPeers peers, int rank, int world, uint32_t epoch) {
-  if (threadIdx.x < world) xg_signal_and_wait(peers, rank, threadIdx.x, epoch);
+__global__ void xg_barrier_kernel(XgPeers peers, int rank, int world, uint32_t epoch, unsigned long long timeout_ns) {
+  if (threadIdx.x < world) xg_signal_and_wait(peers, rank, threadIdx.x, epoch, timeout_ns);
 }
 
 // Tail of a multi-CTA exchange kernel: the last CTA to get here runs the barrier, so the kernel (and with it
 // the stream) completes only when every rank's data has landed.
-__device__ __forceinline__ void xg_tail_barrier(const XgPeers& peers, int rank, int world, uint32_t epoch) {
+__device__ __forceinline__ void xg_tail_barrier(const XgPeers& peers, int rank, int world, uint32_t epoch,
+                                                unsigned long long timeout_ns) {
   __shared__ int is_last;
   __threadfence_system();  // my stores (peer windows included) before the count
   __syncthreads();
@@ -93,12 +109,12 @@ __device__ __forceinline__ void xg_tail_barrier(const XgPeers& peers, int rank, 
     if (is_last) hdr[XG_W_COUNT] = 0;  // ready for the next launch (stream-ordered)
   }
   __syncthreads();
-  if (is_last && threadIdx.x < world) xg_signal_and_wait(peers, rank, threadIdx.x, epoch);
+  if (is_last && threadIdx.x < world) xg_signal_and_wait(peers, rank, threadIdx.x, epoch, timeout_ns);
 }
 
 // my slice of a column-indexed result -> the same offset in every peer's window, then the barrier
 __global__ void __launch_bounds__(256) xg_push_kernel(XgPeers peers, int rank, int world, size_t off_bytes, int64_t n,
-                                                       uint32_t epoch) {
+                                                       uint32_t epoch, unsigned long long timeout_ns) {
   const double* __restrict__ src = reinterpret_cast<const double*>(peers.base[rank] + off_bytes);
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride) {
@@ -106,7 +122,7 @@ __global__ void __launch_bounds__(256) xg_push_kernel(XgPeers peers, int rank, i
     for (int q = 0; q < world; ++q)
       if (q != rank) reinterpret_cast<double*>(peers.base[q] + off_bytes)[k] = v;
   }
-  xg_tail_barrier(peers, rank, world, epoch);
+  xg_tail_barrier(peers, rank, world, epoch, timeout_ns);
 }
 
 // The whole row exchange in one launch.  CTA 0 runs barrier `epoch` (every rank's partial is complete) and
@@ -116,19 +132,24 @@ __global__ void __launch_bounds__(256) xg_push_kernel(XgPeers peers, int rank, i
 template <int WORLD>
 __global__ void __launch_bounds__(256) xg_reduce_kernel(XgPeers peers, int rank, int world, size_t partial_off,
                                                          size_t result_off, int64_t r0, int64_t r1, double divisor,
-                                                         uint32_t epoch) {
+                                                         uint32_t epoch, unsigned long long timeout_ns) {
   uint32_t* hdr = reinterpret_cast<uint32_t*>(peers.base[rank]);
   if (blockIdx.x == 0) {
-    if (threadIdx.x < world) xg_signal_and_wait(peers, rank, threadIdx.x, epoch);
+    if (threadIdx.x < world) xg_signal_and_wait(peers, rank, threadIdx.x, epoch, timeout_ns);
     __syncthreads();
     if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(hdr + XG_W_GO), "r"(epoch) : "memory");
   } else {
     if (threadIdx.x == 0) {
+      // CTA 0 of this launch opens the gate once every rank's partial is complete.  It is resident (launched
+      // first) or becomes resident as soon as a slot frees up; like the barrier itself the wait has no early exit —
+      // it gives up by trapping, never by going on with partials that may be incomplete.
       uint32_t v;
-      const long long t0 = clock64();
+      const unsigned long long t0 = global_ns();
+      unsigned spins = 0;
       for (;;) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(hdr + XG_W_GO) : "memory");
-        if (static_cast<int32_t>(v - epoch) >= 0 || clock64() - t0 > 10000000000LL) break;
+        if (static_cast<int32_t>(v - epoch) >= 0) break;
+        if ((++spins & 255u) == 0u && global_ns() - t0 > timeout_ns + timeout_ns / 4) xg_give_up(peers, rank, 0xC0000000u);
         __nanosleep(200);  // a sweep may be running beside this kernel: do not hammer the L2 slice of the gate word
       }
     }
@@ -194,7 +215,7 @@ __global__ void __launch_bounds__(256) xg_reduce_kernel(XgPeers peers, int rank,
     if (divisor != 0.0) acc = __ddiv_rn(acc, divisor);
     for (int q = 0; q < nw; ++q) reinterpret_cast<double*>(peers.base[q] + result_off)[k] = acc;
   }
-  xg_tail_barrier(peers, rank, world, epoch + 1);
+  xg_tail_barrier(peers, rank, world, epoch + 1, timeout_ns);
 }
 
 int check_xg(const sb200_exchange* x, bool need_connected) {
@@ -230,9 +251,21 @@ void configure_kernels() {
   prefer_max_shared(xg_reduce_kernel<8>);
 }
 
+unsigned long long exchange_timeout_ns() {
+  static const unsigned long long ns = [] {
+    double sec = 600.0;
+    if (const char* e = getenv("SB200_EXCHANGE_TIMEOUT_S")) {
+      const double v = atof(e);
+      if (v > 0.0) sec = v;
+    }
+    return static_cast<unsigned long long>(sec * 1e9);
+  }();
+  return ns;
+}
+
 int launch_barrier(sb200_exchange* x, cudaStream_t st) {
   x->epoch += 1;
-  xg_barrier_kernel<<<1, 32, 0, st>>>(x->peers, x->rank, x->world, x->epoch);
+  xg_barrier_kernel<<<1, 32, 0, st>>>(x->peers, x->rank, x->world, x->epoch, exchange_timeout_ns());
   count_launch();
   SB_CUDA(cudaGetLastError());
   return SB200_OK;
@@ -351,7 +384,7 @@ int sb200_exchange_gather(sb200_exchange* x, void* cuda_stream, int64_t full_off
     if (blocks > 296) blocks = 296;
     if (blocks < 1) blocks = 1;  // an empty slice still takes part in the barrier
     x->epoch += 1;
-    xg_push_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x->peers, x->rank, x->world, off, slice_len, x->epoch);
+    xg_push_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x->peers, x->rank, x->world, off, slice_len, x->epoch, exchange_timeout_ns());
     count_launch();
     SB_CUDA(cudaGetLastError());
   }
@@ -376,11 +409,12 @@ int sb200_exchange_reduce(sb200_exchange* x, void* cuda_stream, int64_t partial_
   const size_t po = static_cast<size_t>(partial_offset), ro = static_cast<size_t>(result_offset);
   const uint32_t e = x->epoch + 1;
   x->epoch += 2;
+  const unsigned long long tmo = exchange_timeout_ns();
   switch (x->world) {
-    case 2: xg_reduce_kernel<2><<<g, 256, 0, st>>>(x->peers, x->rank, 2, po, ro, r0, r1, divisor, e); break;
-    case 4: xg_reduce_kernel<4><<<g, 256, 0, st>>>(x->peers, x->rank, 4, po, ro, r0, r1, divisor, e); break;
-    case 8: xg_reduce_kernel<8><<<g, 256, 0, st>>>(x->peers, x->rank, 8, po, ro, r0, r1, divisor, e); break;
-    default: xg_reduce_kernel<0><<<g, 256, 0, st>>>(x->peers, x->rank, x->world, po, ro, r0, r1, divisor, e); break;
+    case 2: xg_reduce_kernel<2><<<g, 256, 0, st>>>(x->peers, x->rank, 2, po, ro, r0, r1, divisor, e, tmo); break;
+    case 4: xg_reduce_kernel<4><<<g, 256, 0, st>>>(x->peers, x->rank, 4, po, ro, r0, r1, divisor, e, tmo); break;
+    case 8: xg_reduce_kernel<8><<<g, 256, 0, st>>>(x->peers, x->rank, 8, po, ro, r0, r1, divisor, e, tmo); break;
+    default: xg_reduce_kernel<0><<<g, 256, 0, st>>>(x->peers, x->rank, x->world, po, ro, r0, r1, divisor, e, tmo); break;
   }
   count_launch();
   SB_CUDA(cudaGetLastError());
@@ -391,7 +425,9 @@ int sb200_exchange_status(sb200_exchange* x) {
   SB_TRY(check_xg(x, false));
   SB_CUDA(cudaSetDevice(x->device));
   uint32_t err = 0;
-  SB_CUDA(cudaMemcpy(&err, x->window + 4 * XG_W_ERROR, sizeof(err), cudaMemcpyDeviceToHost));
+  const cudaError_t ce = cudaMemcpy(&err, x->window + 4 * XG_W_ERROR, sizeof(err), cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess)  // a barrier that gave up traps its kernel: the context reports it from then on
+    return cuda_fail(ce, "exchange status (an exchange barrier may have given up waiting for a peer and trapped)", __FILE__, __LINE__);
   if (err != 0)
     return fail(SB200_E_CUDA, "exchange barrier timed out waiting for rank " + std::to_string(err & 0xffffu) +
                                   " (a peer process died or skipped a collective call)");

@@ -139,6 +139,50 @@ def test_synth_transpose_bit_exact(synth_case, checker):
     A.release()
 
 
+@pytest.mark.parametrize("cfg", ["256x4096:1", "256x4096:4", "512x3072:2"])
+def test_transpose_chunk_sort_placement_on_every_shape(synth_case, cfg, monkeypatch, checker):
+    """The chunk-sorting placement kernel (transpose.cu) forced on every synthetic shape — also the tall ones the
+    library would give to the banded two-pass kernel — in both block geometries and with 1, 2 and 4 columns per
+    thread and chunk: bit-exact whatever the geometry."""
+    name, spec, i, p, x = synth_case
+    geom, kcols = cfg.split(":")
+    monkeypatch.setenv("SB200_TRANSPOSE_PATH", "place")
+    monkeypatch.setenv("SB200_TRANSPOSE_CFG", geom)
+    monkeypatch.setenv("SB200_TRANSPOSE_KCOLS", kcols)
+    with DeviceMatrix.from_host(i, p, x, spec.nrow, spec.ncol) as D:
+        for _ in range(2):  # the second call reuses the plan kept on the handle
+            ti, tp, tx = D.transpose_host()
+            wi, wp, wx = checker.transpose(i, p, x, spec.nrow, spec.ncol)
+            assert np.array_equal(tp, wp) and np.array_equal(ti, wi) and np.array_equal(bits(tx), bits(wx)), (name, cfg)
+        assert D.layouts() & 8
+
+
+@pytest.mark.parametrize("kcols", ["1", "4"])
+@pytest.mark.parametrize("bands", ["3", "40"])
+def test_transpose_chunks_larger_than_the_image(bands, kcols, monkeypatch, checker):
+    """Half-dense matrix, few wide bands: a chunk's runs hold many times the 4096 entries of the shared-memory image,
+    so every chunk is placed in several rounds; the forced banded path must give the same bits."""
+    spec = synth.uniform_spec(1000, 2000, 0.5, 93)
+    i, p, x = synth.generate_host(spec)
+    want = checker.transpose(i, p, x, spec.nrow, spec.ncol)
+    monkeypatch.setenv("SB200_TRANSPOSE_BANDS", bands)
+    monkeypatch.setenv("SB200_TRANSPOSE_KCOLS", kcols)
+    for path in ("place", "banded"):
+        monkeypatch.setenv("SB200_TRANSPOSE_PATH", path)
+        with DeviceMatrix.from_host(i, p, x, spec.nrow, spec.ncol) as D:
+            ti, tp, tx = D.transpose_host()
+        assert np.array_equal(tp, want[1]) and np.array_equal(ti, want[0]) and np.array_equal(bits(tx), bits(want[2])), path
+
+
+def test_transpose_golden_edges_on_both_paths(golden, monkeypatch):
+    g = golden
+    for path in ("place", "banded"):
+        monkeypatch.setenv("SB200_TRANSPOSE_PATH", path)
+        with DeviceMatrix.from_host(g["i"], g["p"], g["x"], g["nrow"], g["ncol"]) as D:
+            ti, tp, tx = D.transpose_host()
+        assert np.array_equal(tp, g["t_p"]) and np.array_equal(ti, g["t_i"]) and np.array_equal(bits(tx), bits(g["t_x"])), path
+
+
 def _columns_of_lengths(lengths, nrow, seed):
     rng = np.random.default_rng(seed)
     p = np.zeros(len(lengths) + 1, np.int64)
@@ -222,12 +266,15 @@ def test_row_indexed_ops_on_both_paths(row_plan, case, monkeypatch, checker):
     A.release()
 
 
+@pytest.mark.parametrize("path", ["banded", "place"])
 @pytest.mark.parametrize("bands", [1, 2, 7, 64, 300])
-def test_transpose_is_independent_of_band_count(bands, monkeypatch, checker):
-    """The band decomposition is an implementation detail: any band count gives the same bits."""
+def test_transpose_is_independent_of_band_count(bands, path, monkeypatch, checker):
+    """The band decomposition is an implementation detail: any band count gives the same bits, with either
+    placement kernel (the library picks by shape; SB200_TRANSPOSE_PATH forces one)."""
     spec = synth.powerlaw_spec(6000, 3000, 300.0, 91, row_levels=8)
     i, p, x = synth.generate_host(spec)
     monkeypatch.setenv("SB200_TRANSPOSE_BANDS", str(bands))
+    monkeypatch.setenv("SB200_TRANSPOSE_PATH", path)
     T = Matrix(x, i, p, np.array([spec.nrow, spec.ncol], np.int32)).transpose()
     ti, tp, tx = checker.transpose(i, p, x, spec.nrow, spec.ncol)
     assert np.array_equal(T.p, tp) and np.array_equal(T.i, ti) and np.array_equal(bits(T.x), bits(tx))
@@ -446,18 +493,20 @@ def test_band_companion_products_on_synthetic_shapes(case, band_rows, monkeypatc
         oracle.assert_within("rowSums", D.row_sums(), checker.rowSums(*args), *args, tol=TOL)
 
 
-@pytest.mark.parametrize("lanes", ["4", "8", "32"])
+@pytest.mark.parametrize("cap", ["8", "16"])
+@pytest.mark.parametrize("ring", ["1024,2", "640,3", "512,4"])
 @pytest.mark.parametrize("regime", ["const_0_1_2", "const_10", "const_100", "const_938_939_940", "long_then_dust", "sawtooth"])
-def test_band_companion_lane_groups_and_run_lengths(regime, lanes, monkeypatch, checker):
-    """Every lane-group width of the band sweep on every run-length regime (the width is normally picked from
-    the mean run length), with 1 band and with 24 bands of 256 rows."""
+def test_band_companion_piece_sizes_rings_and_run_lengths(regime, ring, cap, monkeypatch, checker):
+    """Both piece sizes (entries a thread sums; normally picked from the mean run length) and every instantiated
+    ring geometry of the band sweep on every run-length regime, with 1 band and with 24 bands of 256 rows."""
     lengths = LENGTH_REGIMES[regime]
     nrow = 6000
     i, p, x = _columns_of_lengths(lengths, nrow, zlib_seed(regime) + 5)
     args = (i, p, x, nrow, len(lengths))
     v_row = synth.dense_vector(11, nrow)
     want = checker.spmv_t(*args, v_row)
-    monkeypatch.setenv("SB200_BS_LANES", lanes)
+    monkeypatch.setenv("SB200_BS_CAP", cap)
+    monkeypatch.setenv("SB200_BS_CFG", ring)
     for rows in (None, "256"):
         if rows:
             monkeypatch.setenv("SB200_BMC_ROWS", rows)
