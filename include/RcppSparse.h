@@ -13,7 +13,8 @@
 //   InnerIterator                                          reference :218-233 (host side, unchanged)
 //   Rcpp::traits::Exporter<RcppSparse::Matrix>             reference :398-423
 // Additions: spmv(v) = A v and spmv_t(v) = A^T v (the reference only has the iterator idiom),
-// refresh() after mutating x in place, release() to drop the device mirror early.
+// resident() to keep the device mirror between calls (then refresh() after mutating x in place, release() to
+// drop it); SB200_GPUS=n runs the sweeps on n GPUs of this process (sb200_sharded_*).
 //   dense copies (operator()(rows, cols), col, row), InnerIndices, emptyInnerIndices, isAppxSymmetric,
 //   InnerIteratorInRange / NotInRange, InnerRowIterator       reference :75-128, :196-216, :238-373 (host side; the
 //   row iterator and the symmetry test do what their interfaces promise — the reference's own walk is broken)
@@ -63,14 +64,28 @@ inline int device_from_env() {
   return e ? std::atoi(e) : 0;
 }
 
-// Owner of one device mirror.  Held through a shared_ptr by the Matrix: copies of a Matrix alias the
-// same R vectors (Rcpp handle semantics), so they share the mirror too; it is destroyed with the last
-// copy.  There is no cache keyed by host address across objects — R may reuse addresses after a GC
-// (SURVEY.md H4); the addresses below only detect that THIS object's members were re-pointed.
+inline int gpus_from_env() {
+  const char* e = std::getenv("SB200_GPUS");
+  const int n = e ? std::atoi(e) : 1;
+  return n < 1 ? 1 : n;
+}
+
+// Owner of the device state of one Matrix.  Held through a shared_ptr: copies of a Matrix alias the same R
+// vectors (Rcpp handle semantics), so they share it too; it is destroyed with the last copy.  There is no cache
+// keyed by host address across objects — R may reuse addresses after a GC.
+//
+// The reference reads x / i / p LIVE on every call (its methods are loops over the R vectors, RcppSparse.h:131-156)
+// and its vignette mutates them in place (Documentation.Rmd:325-347).  So by default nothing outlives a call here
+// either: every method uploads the slots as they are NOW, runs, and drops the mirror — exactly what a fresh Matrix per
+// .Call pays anyway (src/RcppExports.cpp:20).  Matrix::resident(true) opts into keeping the mirror (and the layouts
+// the library caches on it) between calls; then an in-place change of x must be followed by refresh(), a change of
+// i / p by release().
 struct Mirror {
-  sb200_matrix* handle = nullptr;
-  // the slots the handle was uploaded from: if the public members are re-pointed afterwards
-  // (m.x = other; the vignette allows it, Documentation.Rmd:235-236) the mirror is rebuilt
+  sb200_matrix* handle = nullptr;    // one GPU
+  sb200_sharded* sharded = nullptr;  // SB200_GPUS > 1: nnz-balanced column blocks on several GPUs of this process
+  bool resident = false;
+  // the slots the handles were uploaded from: if the public members are re-pointed afterwards
+  // (m.x = other; the vignette allows it, Documentation.Rmd:235-236) a resident mirror is rebuilt
   const void *src_x = nullptr, *src_i = nullptr, *src_p = nullptr;
   long src_nnz = -1;
   int src_nrow = -1, src_ncol = -1;
@@ -79,7 +94,9 @@ struct Mirror {
   Mirror& operator=(const Mirror&) = delete;
   void drop() {
     if (handle) sb200_matrix_destroy(handle);
+    if (sharded) sb200_sharded_destroy(sharded);
     handle = nullptr;
+    sharded = nullptr;
   }
   ~Mirror() { drop(); }
 };
@@ -210,32 +227,37 @@ public:
     return true;
   }
 
-  // ---- the sweeps: one kernel launch each behind the C ABI --------------------------------------------
+  // ---- the sweeps: one kernel launch each behind the C ABI (per GPU when SB200_GPUS > 1) --------------------
   Rcpp::NumericVector colSums() {
     Rcpp::NumericVector sums(Dim[1]);
-    b200::check(sb200_col_sums(mirror(), sums.begin()));
+    Lease l(*this, true);
+    b200::check(l.s ? sb200_sharded_col_sums(l.s, sums.begin()) : sb200_col_sums(l.m, sums.begin()));
     return sums;
   }
   Rcpp::NumericVector rowSums() {
     Rcpp::NumericVector sums(Dim[0]);
-    b200::check(sb200_row_sums(mirror(), sums.begin()));
+    Lease l(*this, true);
+    b200::check(l.s ? sb200_sharded_row_sums(l.s, sums.begin()) : sb200_row_sums(l.m, sums.begin()));
     return sums;
   }
   Rcpp::NumericVector colMeans() {
     Rcpp::NumericVector means(Dim[1]);
-    b200::check(sb200_col_means(mirror(), means.begin()));
+    Lease l(*this, true);
+    b200::check(l.s ? sb200_sharded_col_means(l.s, means.begin()) : sb200_col_means(l.m, means.begin()));
     return means;
   }
   Rcpp::NumericVector rowMeans() {
     Rcpp::NumericVector means(Dim[0]);
-    b200::check(sb200_row_means(mirror(), means.begin()));
+    Lease l(*this, true);
+    b200::check(l.s ? sb200_sharded_row_means(l.s, means.begin()) : sb200_row_means(l.m, means.begin()));
     return means;
   }
 
   // dense A^T A (reference :158-194): ncol x ncol, exactly symmetric -> sb200_crossprod
   Rcpp::NumericMatrix crossprod() {
     Rcpp::NumericMatrix res(Dim[1], Dim[1]);
-    b200::check(sb200_crossprod(mirror(), res.begin()));
+    Lease l(*this, false);
+    b200::check(sb200_crossprod(l.m, res.begin()));
     return res;
   }
 
@@ -243,13 +265,15 @@ public:
   Rcpp::NumericVector spmv(const Rcpp::NumericVector& v) {
     if (v.size() != Dim[1]) throw std::invalid_argument("spmv: v must have ncol entries");
     Rcpp::NumericVector y(Dim[0]);
-    b200::check(sb200_spmv(mirror(), v.begin(), y.begin()));
+    Lease l(*this, true);
+    b200::check(l.s ? sb200_sharded_spmv(l.s, v.begin(), y.begin()) : sb200_spmv(l.m, v.begin(), y.begin()));
     return y;
   }
   Rcpp::NumericVector spmv_t(const Rcpp::NumericVector& v) {
     if (v.size() != Dim[0]) throw std::invalid_argument("spmv_t: v must have nrow entries");
     Rcpp::NumericVector y(Dim[1]);
-    b200::check(sb200_spmv_t(mirror(), v.begin(), y.begin()));
+    Lease l(*this, true);
+    b200::check(l.s ? sb200_sharded_spmv_t(l.s, v.begin(), y.begin()) : sb200_spmv_t(l.m, v.begin(), y.begin()));
     return y;
   }
 
@@ -260,7 +284,8 @@ public:
     Rcpp::NumericVector tx(nnz);
     tdim[0] = Dim[1];
     tdim[1] = Dim[0];
-    b200::check(sb200_transpose(mirror(), tp.begin(), ti.begin(), tx.begin()));
+    Lease l(*this, false);
+    b200::check(sb200_transpose(l.m, tp.begin(), ti.begin(), tx.begin()));
     return Matrix(tx, ti, tp, tdim);
   }
   Matrix t() { return transpose(); }
@@ -274,9 +299,27 @@ public:
     return s;
   }
 
-  // The view aliases R memory; after changing x in place call refresh() so the mirror follows.
+  // Keep the device mirror (and the layouts the library caches on it) between calls instead of re-reading the R
+  // vectors on every call like the reference does.  From then on: after changing x in place call refresh(), after
+  // changing i / p call release().
+  void resident(bool on = true) {
+    mirror_->resident = on;
+    if (!on) mirror_->drop();
+  }
+  bool is_resident() const { return mirror_->resident; }
+  // re-upload x into a resident mirror (no-op otherwise: non-resident calls read x live)
   void refresh() {
     if (mirror_->handle) b200::check(sb200_matrix_refresh_values(mirror_->handle, x.begin()));
+    if (mirror_->sharded) {  // the blocks are contiguous slices of x
+      int n = 0;
+      std::vector<int64_t> bounds(17, 0);
+      b200::check(sb200_sharded_info(mirror_->sharded, &n, bounds.data()));
+      for (int k = 0; k < n; ++k) {
+        sb200_matrix* blk = nullptr;
+        b200::check(sb200_sharded_block(mirror_->sharded, k, &blk));
+        b200::check(sb200_matrix_refresh_values(blk, x.begin() + p[bounds[k]]));
+      }
+    }
   }
   void release() { mirror_->drop(); }
 
@@ -410,27 +453,44 @@ private:
   // Matrix aliases the same R vectors and must see the same device state.
   std::shared_ptr<b200::Mirror> mirror_;
 
-  // one-time upload of i/p/x (pinned in place for the copy), tied to this object and its copies
-  sb200_matrix* mirror() {
-    b200::Mirror& m = *mirror_;
-    const bool same = m.handle && m.src_x == static_cast<const void*>(x.begin()) &&
-                      m.src_i == static_cast<const void*>(i.begin()) && m.src_p == static_cast<const void*>(p.begin()) &&
-                      m.src_nnz == long(x.size()) && m.src_nrow == Dim[0] && m.src_ncol == Dim[1];
-    if (!same) {
-      m.drop();
-      if (Dim.size() != 2 || p.size() != long(Dim[1]) + 1 || i.size() != x.size())
+  // The device handle(s) for one call: uploaded from the slots as they are now, dropped again at the end of the call
+  // unless the Matrix is resident.  multi = the op has a several-GPU form (the sweeps; not transpose / crossprod).
+  struct Lease {
+    b200::Mirror& mm;
+    sb200_matrix* m = nullptr;
+    sb200_sharded* s = nullptr;
+    Lease(Matrix& A, bool multi) : mm(*A.mirror_) {
+      const int gpus = multi ? b200::gpus_from_env() : 1;
+      const bool same = mm.src_x == static_cast<const void*>(A.x.begin()) && mm.src_i == static_cast<const void*>(A.i.begin()) &&
+                        mm.src_p == static_cast<const void*>(A.p.begin()) && mm.src_nnz == long(A.x.size()) &&
+                        mm.src_nrow == A.Dim[0] && mm.src_ncol == A.Dim[1];
+      if (!mm.resident || !same) mm.drop();
+      if (A.Dim.size() != 2 || A.p.size() != long(A.Dim[1]) + 1 || A.i.size() != A.x.size())
         throw std::invalid_argument("RcppSparse::Matrix: slot lengths inconsistent with Dim");
-      b200::check(sb200_matrix_create(i.begin(), p.begin(), x.begin(), Dim[0], Dim[1], x.size(),
-                                      b200::device_from_env(), 0u, &m.handle));
-      m.src_x = x.begin();
-      m.src_i = i.begin();
-      m.src_p = p.begin();
-      m.src_nnz = long(x.size());
-      m.src_nrow = Dim[0];
-      m.src_ncol = Dim[1];
+      if (gpus > 1) {
+        if (!mm.sharded)
+          b200::check(sb200_sharded_create(A.i.begin(), A.p.begin(), A.x.begin(), A.Dim[0], A.Dim[1], A.x.size(), gpus, nullptr, 0u,
+                                           &mm.sharded));
+        s = mm.sharded;
+      } else {
+        if (!mm.handle)
+          b200::check(sb200_matrix_create(A.i.begin(), A.p.begin(), A.x.begin(), A.Dim[0], A.Dim[1], A.x.size(),
+                                          b200::device_from_env(), 0u, &mm.handle));
+        m = mm.handle;
+      }
+      mm.src_x = A.x.begin();
+      mm.src_i = A.i.begin();
+      mm.src_p = A.p.begin();
+      mm.src_nnz = long(A.x.size());
+      mm.src_nrow = A.Dim[0];
+      mm.src_ncol = A.Dim[1];
     }
-    return m.handle;
-  }
+    ~Lease() {
+      if (!mm.resident) mm.drop();
+    }
+    Lease(const Lease&) = delete;
+    Lease& operator=(const Lease&) = delete;
+  };
 };
 
 }  // namespace RcppSparse

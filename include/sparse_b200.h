@@ -180,6 +180,28 @@ int sb200_exchange_barrier(sb200_exchange* x, void* cuda_stream);
  * stream and every later CUDA call fail, no result computed from partial data is ever returned. */
 int sb200_exchange_status(sb200_exchange* x);
 
+/* ---- one process, several GPUs (SURVEY.md 8e behind the shim) --------------------------------------------------
+ * The reference is ONE R process calling Matrix methods (RcppSparse.h:131-156); a drop-in cannot be launched as one
+ * process per GPU.  sb200_sharded_create cuts the dgCMatrix into n_gpus nnz-balanced contiguous column blocks
+ * (columns are independent units; a block is a dgCMatrix with the full row count), uploads block k to devices[k]
+ * (NULL = devices 0..n_gpus-1; the devices need peer access to each other when n_gpus > 1) and returns one handle.
+ * The ops take and fill HOST vectors like the single-GPU entry points: column-indexed results are disjoint slices
+ * copied straight to their place; row-indexed results are full-length partials summed in block order by the
+ * library's P2P reduction kernel on all devices at once (bit-identical run to run for deterministic partials).
+ * The drop-in header uses this form when SB200_GPUS > 1.  Error behaviour as sb200_matrix_create. */
+typedef struct sb200_sharded sb200_sharded;
+int sb200_sharded_create(const int32_t* i, const int32_t* p, const double* x, int32_t nrow, int32_t ncol, int64_t nnz,
+                         int n_gpus, const int* devices, unsigned flags, sb200_sharded** out);
+int sb200_sharded_destroy(sb200_sharded* s);
+int sb200_sharded_info(const sb200_sharded* s, int* n_gpus, int64_t* bounds /* n_gpus + 1 first columns, or NULL */);
+int sb200_sharded_block(const sb200_sharded* s, int k, sb200_matrix** block /* borrowed: block k's mirror */);
+int sb200_sharded_col_sums(sb200_sharded* s, double* out /* ncol */);
+int sb200_sharded_row_sums(sb200_sharded* s, double* out /* nrow */);
+int sb200_sharded_col_means(sb200_sharded* s, double* out /* ncol */);
+int sb200_sharded_row_means(sb200_sharded* s, double* out /* nrow */);
+int sb200_sharded_spmv(sb200_sharded* s, const double* v /* ncol */, double* y /* nrow */);
+int sb200_sharded_spmv_t(sb200_sharded* s, const double* v /* nrow */, double* y /* ncol */);
+
 /* Scratch, results and cached layouts come from the device's stream-ordered memory pool, which keeps freed blocks
  * for reuse (a multi-GB cudaMalloc/cudaFree pair costs as much as a sweep).  sb200_trim synchronises the device and
  * hands everything the pool holds but does not use back to the driver (e.g. before another library allocates). */

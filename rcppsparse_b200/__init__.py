@@ -5,6 +5,6 @@ Only what the path needs: ``csrc/`` (sm_100a CUDA kernels + the C ABI of libspar
 sharding across ranks), ``synth`` (deterministic dgCMatrix generators for tests and benchmarks).
 """
 from ._lib import SparseB200Error
-from .matrix import DeviceMatrix, Matrix, columnSums
+from .matrix import DeviceMatrix, Matrix, ShardedHostMatrix, columnSums
 
-__all__ = ["Matrix", "DeviceMatrix", "columnSums", "SparseB200Error"]
+__all__ = ["Matrix", "DeviceMatrix", "ShardedHostMatrix", "columnSums", "SparseB200Error"]

@@ -110,19 +110,32 @@ struct BsMeta {
 };
 
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(BS_GROUP) : "memory"); }
+// try_wait with a suspend-time hint: the thread sleeps in hardware (no issue slots) until the phase completes or
+// the hint (ns) runs out
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(ptx::smem_addr(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+
 // L2 prefetch of a byte range (cp.async.bulk.prefetch.L2: no shared memory, no completion to wait for)
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 // One tile, one consumer group of 128 threads:
-//   pieces  a run of up to cap / 2 cap / 4 cap entries is cut into 1 / 2 / 4 PIECES that interleave (piece p takes
-//           the run's entries p, p + np, p + 2 np, ...: neighbouring lanes read neighbouring entries); one packed
-//           32-bit descriptor per piece, slots handed out by a warp scan + one shared-memory atomic per warp;
-//           longer runs go to a short list and are summed by all 128 threads together, one reduction per warp;
-//   sums    a THREAD per piece walks its <= cap entries: x from the stage, the row id from the stage, the
-//           operand from the band slice, one FMA — ~7 instructions per entry and nothing per run but the
-//           descriptor and one red.global.add.f64 on y[column].
+//   a THREAD per run: up to cap (16) entries are summed on the spot — x and the row id from the stage, the operand
+//   from the band slice, one FMA per entry, one red.global.add.f64 on y[column] per run, nothing else per run but
+//   its two bounds.  A run of up to 2 / 4 cap entries is cut into 2 / 4 interleaved PIECES (piece p takes entries
+//   p, p + np, ...: neighbouring lanes read neighbouring entries): its thread sums piece 0 and queues the others as
+//   packed 32-bit descriptors, summed a thread per piece after the group's barrier.  Longer runs go to a short
+//   list and are summed by all 128 threads together, one reduction per warp.
 // (Round 2's first version summed a run with a group of 4-32 lanes: ~100 instructions per entry at 12 entries per
 // run — shuffles, bounds and loop overhead per run per lane; ncu: 317 M warp instructions for 1e8 entries.)
 template <int TILE, int STAGES>
@@ -237,8 +250,9 @@ __global__ void __launch_bounds__(BS_THREADS, 1) bandsweep_kernel(const BsParams
           const int32_t r_cnt = (mt.nk > 0) ? (((k1 - r_al) + 7) & ~7) : 0;
           mt.r_off = k0 - r_al;
           mt.pad = 0;
-          if (seq >= STAGES) {  // the stage is still being read: wait without stealing the consumers' issue slots
-            while (!ptx::mbar_try_wait(&empty_bar[g][s], ((seq / STAGES) - 1u) & 1u)) __nanosleep(128);
+          if (seq >= STAGES) {  // the stage is still being read: sleep in hardware until the group hands it back
+            while (!mbar_try_wait_suspend(&empty_bar[g][s], ((seq / STAGES) - 1u) & 1u, 1000000u)) {
+            }
           }
           meta[g][s] = mt;
           unsigned char* st = my_stages + static_cast<size_t>(s) * G::STAGE_BYTES;
@@ -283,8 +297,9 @@ __global__ void __launch_bounds__(BS_THREADS, 1) bandsweep_kernel(const BsParams
         const uint16_t* __restrict__ rs = reinterpret_cast<const uint16_t*>(st + G::X_BYTES + G::A_BYTES) + mt.r_off;
         double* __restrict__ yb = prm.y + mt.c0;
         const int nseg = mt.nc + 1;  // runs c0 .. c0+nc-1 end in the tile, the last one stays open (may be empty)
-        // ---- pieces --------------------------------------------------------------------------------------
-        // np = 1, 2 or 4 pieces per run (a power of two: no division); longer runs go to the long list
+        // ---- a thread per run: runs of up to `cap` entries are summed on the spot by their thread; a run of up to
+        //      2 / 4 cap is cut into 2 / 4 interleaved pieces — the thread sums piece 0 and queues the others;
+        //      longer runs go to the long list.  Nothing per run but its two bounds and one reduction. -------------
         for (int base = 0; base < nseg; base += BS_GROUP) {  // trip count uniform over the group
           const int seg = base + tg;
           int beg = 0, len = 0;
@@ -292,31 +307,33 @@ __global__ void __launch_bounds__(BS_THREADS, 1) bandsweep_kernel(const BsParams
             beg = (seg == 0) ? 0 : as[seg - 1] - mt.k0;
             len = ((seg == mt.nc) ? mt.nk : as[seg] - mt.k0) - beg;
           }
-          const bool is_long = len > (cap << 2);
-          const int lg = (len > (cap << 1)) ? 2 : ((len > cap) ? 1 : 0);
-          const int np = (len <= 0 || is_long) ? 0 : (1 << lg);
-          if (is_long) {
+          if (len > (cap << 2)) {
             const int slot = atomicAdd(&long_cnt[g][par], 1);
             long_list[g][par][slot][0] = beg;
             long_list[g][par][slot][1] = len;
             long_list[g][par][slot][2] = seg;
+          } else if (len > 0) {
+            const int lg = (len > (cap << 1)) ? 2 : ((len > cap) ? 1 : 0);
+            const int np = 1 << lg;
+            if (lg) {
+              uint32_t* dst = pieces + atomicAdd(&piece_cnt[g][par], np - 1);
+              const uint32_t common = (static_cast<uint32_t>(lg) << 10) | (static_cast<uint32_t>(seg) << 21);
+              for (int p = 1; p < np; ++p)
+                dst[p - 1] = static_cast<uint32_t>(beg + p) | common | (static_cast<uint32_t>((len - 1 - p) >> lg) << 17);  // count - 1
+            }
+            int cnt = ((len - 1) >> lg) + 1;
+            int k = beg;
+            double a0 = 0.0, a1 = 0.0;
+            for (; cnt >= 2; cnt -= 2, k += 2 * np) {
+              a0 = __fma_rn(xs[k], vs[rs[k]], a0);
+              a1 = __fma_rn(xs[k + np], vs[rs[k + np]], a1);
+            }
+            if (cnt) a0 = __fma_rn(xs[k], vs[rs[k]], a0);
+            ptx::red_add_f64(yb + seg, __dadd_rn(a0, a1));
           }
-          int incl = np;
-#pragma unroll
-          for (int off = 1; off < 32; off <<= 1) {
-            const int up = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += up;
-          }
-          int slot0 = 0;
-          if (lane == 31 && incl > 0) slot0 = atomicAdd(&piece_cnt[g][par], incl);
-          slot0 = __shfl_sync(0xffffffffu, slot0, 31);
-          uint32_t* dst = pieces + slot0 + incl - np;
-          const uint32_t common = (static_cast<uint32_t>(lg) << 10) | (static_cast<uint32_t>(seg) << 21);
-          for (int p = 0; p < np; ++p)
-            dst[p] = static_cast<uint32_t>(beg + p) | common | (static_cast<uint32_t>((len - 1 - p) >> lg) << 17);  // count - 1
         }
         group_sync(1 + g);
-        // ---- sums: a thread per piece -------------------------------------------------------------------------
+        // ---- the queued pieces: a thread per piece ------------------------------------------------------------
         const int P = piece_cnt[g][par];
         for (int w = tg; w < P; w += BS_GROUP) {
           const uint32_t d = pieces[w];

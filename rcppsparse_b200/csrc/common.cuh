@@ -162,6 +162,9 @@ int build_row_companion(sb200_matrix* m);  // capi.cu; non-fatal: leaves rows_st
 void drop_row_companion(sb200_matrix* m);
 int row_companion_after();                 // SB200_ROW_COMPANION_AFTER (default 8, 0 = never build on its own)
 
+// exchange.cu (single-process form used by sharded.cu)
+int exchange_connect_local(sb200_exchange** xs, int world);
+unsigned char* exchange_window_base(const sb200_exchange* x);
 // mirror.cu
 int alloc_matrix(int device, int32_t nrow, int32_t ncol, int64_t nnz, sb200_matrix** out);  // owns arrays, uninitialised
 int finish_matrix(sb200_matrix* m, unsigned flags);  // validate + plan + workspace

@@ -39,6 +39,7 @@ struct sb200_exchange {
   size_t bytes;  // whole window, header included
   unsigned char* window;
   bool connected;
+  bool local;  // peers are windows of this same process (sb200_sharded): plain device pointers, nothing to unmap
   sb200::XgPeers peers;
   uint32_t epoch;
 };
@@ -344,7 +345,7 @@ int sb200_exchange_destroy(sb200_exchange* x) {
   SB_TRY(check_xg(x, false));
   cudaSetDevice(x->device);
   cudaDeviceSynchronize();
-  if (x->connected)
+  if (x->connected && !x->local)
     for (int q = 0; q < x->world; ++q)
       if (q != x->rank && x->peers.base[q]) cudaIpcCloseMemHandle(x->peers.base[q]);
   cudaFree(x->window);
@@ -353,6 +354,42 @@ int sb200_exchange_destroy(sb200_exchange* x) {
   delete x;
   return SB200_OK;
 }
+
+}  // extern "C"
+
+namespace sb200 {
+// Single-process form (sharded.cu): the windows of xs[0..world) belong to this process, one per device; every device
+// gets peer access to every other and the windows are addressed directly (unified addressing), no cudaIpc.
+int exchange_connect_local(sb200_exchange** xs, int world) {
+  if (world < 1 || world > XG_MAX_RANKS) return fail(SB200_E_INVALID, "exchange: at most 16 devices");
+  for (int r = 0; r < world; ++r) SB_TRY(check_xg(xs[r], false));
+  for (int r = 0; r < world; ++r) {
+    SB_CUDA(cudaSetDevice(xs[r]->device));
+    for (int q = 0; q < world; ++q) {
+      if (q == r || xs[q]->device == xs[r]->device) continue;
+      int can = 0;
+      SB_CUDA(cudaDeviceCanAccessPeer(&can, xs[r]->device, xs[q]->device));
+      if (!can) return fail(SB200_E_UNSUPPORTED, "exchange: devices " + std::to_string(xs[r]->device) + " and " +
+                                                     std::to_string(xs[q]->device) + " have no peer access");
+      const cudaError_t e = cudaDeviceEnablePeerAccess(xs[q]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+      cudaGetLastError();
+    }
+  }
+  configure_kernels();
+  for (int r = 0; r < world; ++r) {
+    for (int q = 0; q < world; ++q) xs[r]->peers.base[q] = xs[q]->window;
+    xs[r]->rank = r;
+    xs[r]->world = world;
+    xs[r]->connected = true;
+    xs[r]->local = true;
+  }
+  return SB200_OK;
+}
+unsigned char* exchange_window_base(const sb200_exchange* x) { return x->window; }
+}  // namespace sb200
+
+extern "C" {
 
 int sb200_exchange_window(const sb200_exchange* x, void** base, int64_t* data_offset, int64_t* bytes) {
   SB_TRY(check_xg(x, false));

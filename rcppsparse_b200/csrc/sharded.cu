@@ -1,0 +1,292 @@
+// One process, several GPUs: the column-sharding layer behind the C ABI.
+//
+// The reference is one R process (zdebruine/RcppSparse; every method of RcppSparse::Matrix, RcppSparse.h:131-156,
+// runs on the calling thread), so a drop-in that wants more than one GPU cannot ask for one process per device.
+// sb200_sharded_create cuts the dgCMatrix into nnz-balanced contiguous column blocks (binary search in p; a block
+// is itself a dgCMatrix with the full row count and p rebased to 0), uploads block k to devices[k] as an ordinary
+// mirror (worker thread per device: each device has its own PCIe link), and gives every device a window of
+// peer-mapped memory.  The ops then run as the same kernels as on one GPU:
+//   column-indexed results (colSums, colMeans, A^T v)  disjoint slices: every device sweeps its block and its slice
+//                                                      goes straight to its place in the caller's host vector;
+//   row-indexed results (rowSums, rowMeans, A v)       full-length partials in the windows, summed in rank order by
+//                                                      the library's own P2P reduction kernel (exchange.cu) running
+//                                                      on every device at once; the mean's division by the GLOBAL
+//                                                      ncol rides in that kernel (RcppSparse.h:154).
+// All launches come from the calling thread, device after device, nothing blocks until the final synchronisation.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+struct sb200_sharded {
+  uint32_t magic;
+  int world;
+  int32_t nrow, ncol;
+  int64_t nnz;
+  std::vector<int> devices;
+  std::vector<int64_t> bounds;  // [world + 1] first column of every block
+  std::vector<sb200_matrix*> blocks;
+  std::vector<sb200_exchange*> windows;
+  int64_t partial_off, result_off;  // byte offsets of the row partial / the row result inside every window
+};
+
+namespace sb200 {
+namespace {
+
+constexpr uint32_t SHARDED_MAGIC = 0x5B2005A4u;
+
+int check_sharded(const sb200_sharded* s) {
+  if (!s || s->magic != SHARDED_MAGIC) return fail(SB200_E_INVALID, "not a live sb200_sharded handle");
+  return SB200_OK;
+}
+
+void destroy_sharded(sb200_sharded* s) {
+  if (!s) return;
+  for (sb200_matrix* m : s->blocks)
+    if (m) sb200_matrix_destroy(m);
+  for (sb200_exchange* x : s->windows)
+    if (x) sb200_exchange_destroy(x);
+  s->magic = 0;
+  delete s;
+}
+
+// column-indexed op: out[bounds[k] .. bounds[k+1]) from device k
+int run_columns(sb200_sharded* s, SweepMode mode, const double* v_host, double divisor, double* out) {
+  if (s->ncol > 0 && !out) return fail(SB200_E_INVALID, "output buffer is NULL");
+  DeviceGuard restore(s->blocks[0]->device);  // the caller's current device is put back on return
+  int rc = SB200_OK;
+  for (int k = 0; k < s->world && rc == SB200_OK; ++k) {
+    sb200_matrix* m = s->blocks[k];
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(SB200_E_CUDA, "cudaSetDevice failed");
+    if (mode == SWEEP_SPMV_T && s->nrow > 0)
+      SB_CUDA(cudaMemcpyAsync(m->d_stage_in, v_host, sizeof(double) * static_cast<size_t>(s->nrow), cudaMemcpyHostToDevice, m->stream));
+    rc = launch_sweep(m, mode, m->d_stage_in, divisor, m->d_stage_out);
+    if (rc == SB200_OK && m->ncol > 0)
+      SB_CUDA(cudaMemcpyAsync(out + s->bounds[k], m->d_stage_out, sizeof(double) * static_cast<size_t>(m->ncol), cudaMemcpyDeviceToHost,
+                              m->stream));
+  }
+  for (int k = 0; k < s->world; ++k) {  // every device is waited for, whatever happened on another
+    DeviceGuard guard(s->blocks[k]->device);
+    const cudaError_t e = cudaStreamSynchronize(s->blocks[k]->stream);
+    if (e != cudaSuccess && rc == SB200_OK) rc = cuda_fail(e, "sharded column sweep", __FILE__, __LINE__);
+  }
+  return rc;
+}
+
+// row-indexed op: partials in the windows, rank-ordered P2P reduction on every device, result read from device 0
+int run_rows(sb200_sharded* s, SweepMode mode, const double* v_host, double divisor, double* out) {
+  if (s->nrow > 0 && !out) return fail(SB200_E_INVALID, "output buffer is NULL");
+  DeviceGuard restore(s->blocks[0]->device);  // the exchange entry points switch devices; put the caller's back on return
+  int rc = SB200_OK;
+  for (int k = 0; k < s->world && rc == SB200_OK; ++k) {
+    sb200_matrix* m = s->blocks[k];
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(SB200_E_CUDA, "cudaSetDevice failed");
+    double* partial = reinterpret_cast<double*>(exchange_window_base(s->windows[k]) + s->partial_off);
+    if (mode == SWEEP_SPMV && m->ncol > 0)
+      SB_CUDA(cudaMemcpyAsync(m->d_stage_in, v_host + s->bounds[k], sizeof(double) * static_cast<size_t>(m->ncol), cudaMemcpyHostToDevice,
+                              m->stream));
+    rc = launch_sweep(m, mode, m->d_stage_in, 0.0, partial);
+  }
+  if (rc == SB200_OK) {
+    if (s->world > 1) {
+      for (int k = 0; k < s->world && rc == SB200_OK; ++k)
+        rc = sb200_exchange_reduce(s->windows[k], s->blocks[k]->stream, s->partial_off, s->result_off, s->nrow, divisor);
+    } else if (divisor != 0.0 && s->nrow > 0) {
+      DeviceGuard guard(s->blocks[0]->device);
+      rc = launch_vec_div(s->blocks[0]->stream, reinterpret_cast<double*>(exchange_window_base(s->windows[0]) + s->partial_off), s->nrow,
+                          divisor);
+    }
+  }
+  if (rc == SB200_OK && s->nrow > 0) {
+    DeviceGuard guard(s->blocks[0]->device);
+    const int64_t off = s->world > 1 ? s->result_off : s->partial_off;
+    SB_CUDA(cudaMemcpyAsync(out, exchange_window_base(s->windows[0]) + off, sizeof(double) * static_cast<size_t>(s->nrow),
+                            cudaMemcpyDeviceToHost, s->blocks[0]->stream));
+  }
+  for (int k = 0; k < s->world; ++k) {
+    DeviceGuard guard(s->blocks[k]->device);
+    const cudaError_t e = cudaStreamSynchronize(s->blocks[k]->stream);
+    if (e != cudaSuccess && rc == SB200_OK) rc = cuda_fail(e, "sharded row sweep", __FILE__, __LINE__);
+  }
+  return rc;
+}
+
+}  // namespace
+}  // namespace sb200
+
+using namespace sb200;
+
+extern "C" {
+
+int sb200_sharded_create(const int32_t* i, const int32_t* p, const double* x, int32_t nrow, int32_t ncol, int64_t nnz, int n_gpus,
+                         const int* devices, unsigned flags, sb200_sharded** out) {
+  if (!out) return fail(SB200_E_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!p || (nnz > 0 && (!i || !x))) return fail(SB200_E_INVALID, "NULL slot array");
+  if (nrow < 0 || ncol < 0 || nnz < 0) return fail(SB200_E_INVALID, "negative dimension");
+  if (n_gpus < 1 || n_gpus > 16) return fail(SB200_E_INVALID, "n_gpus must be 1..16 (the GPUs of one node)");
+  int have = 0;
+  if (cudaGetDeviceCount(&have) != cudaSuccess || have <= 0) {
+    cudaGetLastError();
+    return fail(SB200_E_NODEVICE, "no CUDA device available: libsparse_b200 has no CPU fallback");
+  }
+  // the host arrays are validated on the device block by block; the split itself needs p[0] = 0, p monotone, p[ncol] = nnz
+  if (p[0] != 0 || p[ncol] != nnz) return fail(SB200_E_STRUCTURE, "p[0] must be 0 and p[ncol] must be nnz");
+  sb200_sharded* s = new (std::nothrow) sb200_sharded();
+  if (!s) return fail(SB200_E_NOMEM, "host allocation failed");
+  s->magic = SHARDED_MAGIC;
+  s->world = n_gpus;
+  s->nrow = nrow;
+  s->ncol = ncol;
+  s->nnz = nnz;
+  s->devices.resize(n_gpus);
+  for (int k = 0; k < n_gpus; ++k) {
+    s->devices[k] = devices ? devices[k] : k;
+    if (s->devices[k] < 0 || s->devices[k] >= have) {
+      destroy_sharded(s);
+      return fail(SB200_E_NODEVICE, "requested CUDA device " + std::to_string(devices ? devices[k] : k) + " not present");
+    }
+  }
+  // nnz-balanced contiguous column blocks: first column whose start offset reaches k * nnz / n
+  s->bounds.assign(n_gpus + 1, 0);
+  for (int k = 1; k < n_gpus; ++k) {
+    const int64_t target = (nnz * k) / n_gpus;
+    int64_t lo = s->bounds[k - 1], hi = ncol;
+    while (lo < hi) {
+      const int64_t mid = lo + ((hi - lo) >> 1);
+      if (p[mid] < target)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    s->bounds[k] = lo;
+  }
+  s->bounds[n_gpus] = ncol;
+  s->blocks.assign(n_gpus, nullptr);
+  s->windows.assign(n_gpus, nullptr);
+  // upload the blocks concurrently: one worker per device
+  std::vector<int> rcs(n_gpus, SB200_OK);
+  std::vector<std::string> errs(n_gpus);
+  std::vector<std::thread> workers;
+  for (int k = 0; k < n_gpus; ++k) {
+    workers.emplace_back([&, k] {
+      const int64_t c0 = s->bounds[k], c1 = s->bounds[k + 1];
+      const int64_t k0 = p[c0], k1 = p[c1];
+      std::vector<int32_t> pk(static_cast<size_t>(c1 - c0) + 1);
+      bool ok = true;
+      for (int64_t c = c0; c <= c1; ++c) {
+        pk[c - c0] = static_cast<int32_t>(p[c] - k0);
+        if (c > c0 && p[c] < p[c - 1]) ok = false;
+      }
+      if (!ok) {
+        rcs[k] = SB200_E_STRUCTURE;
+        errs[k] = "p is not monotone";
+        return;
+      }
+      rcs[k] = sb200_matrix_create(i + k0, pk.data(), x + k0, nrow, static_cast<int32_t>(c1 - c0), k1 - k0, s->devices[k], flags,
+                                   &s->blocks[k]);
+      if (rcs[k] != SB200_OK) errs[k] = sb200_last_error();
+    });
+  }
+  for (auto& w : workers) w.join();
+  for (int k = 0; k < n_gpus; ++k)
+    if (rcs[k] != SB200_OK) {
+      const int rc = rcs[k];
+      const std::string msg = "column block " + std::to_string(k) + " (device " + std::to_string(s->devices[k]) + "): " + errs[k];
+      destroy_sharded(s);
+      return fail(rc, msg);
+    }
+  // windows: [row partial | row result], 256-byte aligned, behind the exchange header
+  const int64_t vec = ((static_cast<int64_t>(nrow > 0 ? nrow : 1) * 8 + 255) / 256) * 256;
+  int rc = SB200_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (int k = 0; k < n_gpus && rc == SB200_OK; ++k) {
+    unsigned char handle[64];
+    rc = sb200_exchange_create(s->devices[k], 2 * vec, &s->windows[k], handle);
+  }
+  if (rc == SB200_OK) rc = exchange_connect_local(s->windows.data(), n_gpus);
+  cudaSetDevice(prev);
+  if (rc != SB200_OK) {
+    const std::string msg = sb200_last_error();
+    destroy_sharded(s);
+    return fail(rc, msg);
+  }
+  void* base = nullptr;
+  int64_t data_off = 0, bytes = 0;
+  sb200_exchange_window(s->windows[0], &base, &data_off, &bytes);
+  s->partial_off = data_off;
+  s->result_off = data_off + vec;
+  *out = s;
+  return SB200_OK;
+}
+
+int sb200_sharded_destroy(sb200_sharded* s) {
+  if (!s) return SB200_OK;
+  SB_TRY(check_sharded(s));
+  int prev = 0;
+  cudaGetDevice(&prev);
+  destroy_sharded(s);
+  cudaSetDevice(prev);
+  return SB200_OK;
+}
+
+int sb200_sharded_info(const sb200_sharded* s, int* n_gpus, int64_t* bounds) {
+  SB_TRY(check_sharded(s));
+  if (n_gpus) *n_gpus = s->world;
+  if (bounds)
+    for (int k = 0; k <= s->world; ++k) bounds[k] = s->bounds[k];
+  return SB200_OK;
+}
+
+int sb200_sharded_block(const sb200_sharded* s, int k, sb200_matrix** block) {
+  SB_TRY(check_sharded(s));
+  if (k < 0 || k >= s->world || !block) return fail(SB200_E_INVALID, "sb200_sharded_block: bad block index");
+  *block = s->blocks[k];
+  return SB200_OK;
+}
+
+int sb200_sharded_col_sums(sb200_sharded* s, double* out) {
+  SB_TRY(check_sharded(s));
+  return run_columns(s, SWEEP_COLSUM, nullptr, 0.0, out);
+}
+int sb200_sharded_col_means(sb200_sharded* s, double* out) {
+  SB_TRY(check_sharded(s));
+  if (s->nrow == 0) {  // RcppSparse.h:148: sums / Dim[0]; 0/0 = NaN there and here
+    for (int32_t c = 0; c < s->ncol; ++c) out[c] = 0.0 / static_cast<double>(s->nrow);
+    return SB200_OK;
+  }
+  return run_columns(s, SWEEP_COLSUM, nullptr, static_cast<double>(s->nrow), out);
+}
+int sb200_sharded_spmv_t(sb200_sharded* s, const double* v, double* y) {
+  SB_TRY(check_sharded(s));
+  if (s->nrow > 0 && !v) return fail(SB200_E_INVALID, "operand vector is NULL");
+  return run_columns(s, SWEEP_SPMV_T, v, 0.0, y);
+}
+int sb200_sharded_row_sums(sb200_sharded* s, double* out) {
+  SB_TRY(check_sharded(s));
+  return run_rows(s, SWEEP_ROWSUM, nullptr, 0.0, out);
+}
+int sb200_sharded_row_means(sb200_sharded* s, double* out) {
+  SB_TRY(check_sharded(s));
+  if (s->ncol == 0) {
+    for (int32_t r = 0; r < s->nrow; ++r) out[r] = 0.0 / static_cast<double>(s->ncol);
+    return SB200_OK;
+  }
+  return run_rows(s, SWEEP_ROWSUM, nullptr, static_cast<double>(s->ncol), out);
+}
+int sb200_sharded_spmv(sb200_sharded* s, const double* v, double* y) {
+  SB_TRY(check_sharded(s));
+  if (s->ncol > 0 && !v) return fail(SB200_E_INVALID, "operand vector is NULL");
+  return run_rows(s, SWEEP_SPMV, v, 0.0, y);
+}
+
+}  // extern "C"

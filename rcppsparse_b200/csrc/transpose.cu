@@ -55,6 +55,7 @@ struct PlaceArgs {
   int max_rows;  // capacity of the per-row tables (even, >= rows of the widest band)
   int kcols;     // columns per thread and chunk (1..PL_KMAX)
   unsigned int* unit_counter;  // zeroed before the launch
+  int prefetch;  // pull the next chunk's runs towards L2 while this one is placed
 };
 
 template <int THREADS, int E>
@@ -72,7 +73,7 @@ __device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src_gmem)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int THREADS, int E>
-__global__ void __launch_bounds__(THREADS, 2) transpose_place_kernel(const PlaceArgs a) {
+__global__ void __launch_bounds__(THREADS, (THREADS * 22 <= 3072 && E <= 2048) ? 4 : ((E <= 2048) ? 3 : 2)) transpose_place_kernel(const PlaceArgs a) {
   constexpr int W = THREADS / 32;
   constexpr int U = 4;
   extern __shared__ __align__(16) unsigned char psm[];
@@ -153,8 +154,10 @@ __global__ void __launch_bounds__(THREADS, 2) transpose_place_kernel(const Place
         if (kk < K && c < c_hi) {
           ns[kk] = band_start(bv, b, c);
           ne[kk] = band_start(bv, b + 1, c);
-          for (int32_t k = ns[kk] & ~31; k < ne[kk]; k += 32) ptx::prefetch_l2(bv.i + k);
-          for (int32_t k = ns[kk] & ~15; k < ne[kk]; k += 16) ptx::prefetch_l2(bv.x + k);
+          if (a.prefetch) {
+            for (int32_t k = ns[kk] & ~31; k < ne[kk]; k += 32) ptx::prefetch_l2(bv.i + k);
+            for (int32_t k = ns[kk] & ~15; k < ne[kk]; k += 16) ptx::prefetch_l2(bv.x + k);
+          }
         }
       }
       const int par = chunk_no & 1;
@@ -304,13 +307,18 @@ int launch_place(sb200_matrix* m, const BandPlan* bp, int32_t* d_i_out, double* 
     if (v >= 1 && v <= PL_KMAX) K = v;
   }
   a.kcols = K;
+  a.prefetch = getenv("SB200_TRANSPOSE_NOPF") ? 0 : 1;
   // the unit counter lives in the handle's workspace, behind the lockstep counters
   a.unit_counter = reinterpret_cast<unsigned int*>(static_cast<unsigned char*>(m->d_ws) + 16 + 4 * 1024 + 8 * 1024 + 2048);
   SB_CUDA(cudaMemsetAsync(a.unit_counter, 0, sizeof(unsigned int), m->stream));
   const size_t smem = G::smem_bytes(a.max_rows);
   auto kern = transpose_place_kernel<THREADS, E>;
   SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  int grid = m->sm_count * 2;
+  int per_sm = static_cast<int>((224 * 1024) / (smem + 1024));
+  if (per_sm > 2048 / THREADS) per_sm = 2048 / THREADS;
+  if (per_sm > 6) per_sm = 6;
+  if (per_sm < 1) per_sm = 1;
+  int grid = m->sm_count * per_sm;
   if (grid > bp->nb * bp->S) grid = bp->nb * bp->S;
   kern<<<grid, THREADS, smem, m->stream>>>(a);
   count_launch();
@@ -404,6 +412,10 @@ int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double
     const char* cfg = getenv("SB200_TRANSPOSE_CFG");
     if (cfg && !strcmp(cfg, "512x3072"))
       rc = launch_place<512, 3072>(m, bp, d_i_out, d_x_out);
+    else if (cfg && !strcmp(cfg, "128x2048"))
+      rc = launch_place<128, 2048>(m, bp, d_i_out, d_x_out);
+    else if (cfg && !strcmp(cfg, "256x2048"))
+      rc = launch_place<256, 2048>(m, bp, d_i_out, d_x_out);
     else
       rc = launch_place<256, 4096>(m, bp, d_i_out, d_x_out);
   } else {

@@ -240,16 +240,103 @@ class DeviceMatrix:
         check(_lib.lib().sb200_synth_vector_dev(self._h, seed, begin, n, _ptr(d_out)))
 
 
+class ShardedHostMatrix:
+    """One process, several GPUs: owner of one ``sb200_sharded*`` (sparse_b200.h) — the dgCMatrix cut into nnz-balanced
+    column blocks, one per device, behind the same host-vector entry points as a single-GPU mirror."""
+
+    def __init__(self, i, p, x, nrow: int, ncol: int, n_gpus: int, devices=None, validate: bool = True):
+        if isinstance(i, np.ndarray) and (i.dtype != np.int32 or p.dtype != np.int32 or x.dtype != np.float64):
+            raise TypeError("dgCMatrix slots are int32 i/p and float64 x (reference RcppSparse.h:29-30)")
+        if int(p.shape[0]) != ncol + 1:
+            raise ValueError("p must have ncol + 1 entries")
+        dev = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        out = C.c_void_p()
+        check(_lib.lib().sb200_sharded_create(_ptr(i), _ptr(p), _ptr(x), nrow, ncol, int(x.shape[0]), int(n_gpus), _ptr(dev),
+                                              0 if validate else _lib.NO_VALIDATE, C.byref(out)))
+        self._h = out
+        self.nrow, self.ncol, self.nnz, self.n_gpus = nrow, ncol, int(x.shape[0]), int(n_gpus)
+
+    def bounds(self):
+        b = np.zeros(self.n_gpus + 1, np.int64)
+        n = C.c_int()
+        check(_lib.lib().sb200_sharded_info(self._h, C.byref(n), _ptr(b)))
+        return b.tolist()
+
+    def block(self, k: int) -> "DeviceMatrix":
+        """Block k's mirror, borrowed (tuning: cached layouts); do not close it."""
+        h = C.c_void_p()
+        check(_lib.lib().sb200_sharded_block(self._h, k, C.byref(h)))
+        d = DeviceMatrix.__new__(DeviceMatrix)
+        d._h, d._keep = h, self
+        nrow, ncol, nnz = C.c_int32(), C.c_int32(), C.c_int64()
+        check(_lib.lib().sb200_matrix_dims(h, C.byref(nrow), C.byref(ncol), C.byref(nnz)))
+        d.nrow, d.ncol, d.nnz = nrow.value, ncol.value, nnz.value
+        d.close = lambda: None
+        return d
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().sb200_sharded_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _vec(self, fn, n, *args):
+        out = np.empty(n, np.float64)
+        check(fn(self._h, *args, _ptr(out)))
+        return out
+
+    def col_sums(self):
+        return self._vec(_lib.lib().sb200_sharded_col_sums, self.ncol)
+
+    def row_sums(self):
+        return self._vec(_lib.lib().sb200_sharded_row_sums, self.nrow)
+
+    def col_means(self):
+        return self._vec(_lib.lib().sb200_sharded_col_means, self.ncol)
+
+    def row_means(self):
+        return self._vec(_lib.lib().sb200_sharded_row_means, self.nrow)
+
+    def spmv(self, v):
+        v = np.ascontiguousarray(v, np.float64)
+        if v.shape[0] != self.ncol:
+            raise ValueError("A v: v must have ncol entries")
+        return self._vec(_lib.lib().sb200_sharded_spmv, self.nrow, _ptr(v))
+
+    def spmv_t(self, v):
+        v = np.ascontiguousarray(v, np.float64)
+        if v.shape[0] != self.nrow:
+            raise ValueError("A^T v: v must have nrow entries")
+        return self._vec(_lib.lib().sb200_sharded_spmv_t, self.ncol, _ptr(v))
+
+
 class Matrix:
     """Python mirror of ``RcppSparse::Matrix`` (reference RcppSparse.h:25-395), hot-path members.
 
     Public members ``x, i, p, Dim`` alias the arrays passed in (no copy), like the Rcpp handles
-    of RcppSparse.h:29-30.  The device mirror is created on first use and tied to THIS object
-    (SURVEY.md H4): it is never cached by host address.  After mutating ``x`` in place
-    (vignettes/Documentation.Rmd:325-347) call ``refresh()``.
+    of RcppSparse.h:29-30.  The reference's methods read those vectors LIVE on every call and its vignette
+    edits them in place (vignettes/Documentation.Rmd:325-347), so by default nothing outlives a call here either:
+    every method uploads the slots as they are now, runs, and drops the device mirror — what a fresh Matrix per
+    ``.Call`` pays anyway (src/RcppExports.cpp:20).  ``resident=True`` (or ``resident()``) keeps the mirror, and
+    the layouts the library caches on it, between calls; it is tied to THIS object (never cached
+    by host address), rebuilt when a member is re-pointed, and after an in-place edit of ``x`` it needs
+    ``refresh()`` (of ``i``/``p``: ``release()``).  ``gpus > 1`` (default: SB200_GPUS) runs the sweeps on that many
+    GPUs of this process (sb200_sharded_*).
     """
 
-    def __init__(self, x=None, i=None, p=None, Dim=None, device: int = 0, pin: bool = False):
+    def __init__(self, x=None, i=None, p=None, Dim=None, device: int = 0, pin: bool = False, resident: bool = False,
+                 gpus: int | None = None):
         # RcppSparse.h:33 (four vectors) and :42 (default)
         self.x = np.zeros(0, np.float64) if x is None else x
         self.i = np.zeros(0, np.int32) if i is None else i
@@ -257,7 +344,12 @@ class Matrix:
         self.Dim = np.zeros(2, np.int32) if Dim is None else np.asarray(Dim, dtype=np.int32)
         self._device = device
         self._pin = pin
+        self._resident = bool(resident)
+        import os as _os
+        self._gpus = max(1, int(gpus if gpus is not None else _os.environ.get("SB200_GPUS", "1")))
         self._dev: DeviceMatrix | None = None
+        self._sharded: ShardedHostMatrix | None = None
+        self._src = None
 
     @classmethod
     def from_S4(cls, s, **kw) -> "Matrix":
@@ -299,7 +391,7 @@ class Matrix:
 
     def clone(self) -> "Matrix":
         """Deep copy of the four vectors (RcppSparse.h:54-60)."""
-        return Matrix(self.x.copy(), self.i.copy(), self.p.copy(), self.Dim.copy(), self._device, self._pin)
+        return Matrix(self.x.copy(), self.i.copy(), self.p.copy(), self.Dim.copy(), self._device, self._pin, self._resident, self._gpus)
 
     def wrap(self):
         """RcppSparse.h:387-394: back to the host language's dgCMatrix (scipy CSC sharing the arrays)."""
@@ -331,52 +423,94 @@ class Matrix:
             return self._col
 
     # ---- device mirror -------------------------------------------------------------------------------------------
-    def _mirror(self) -> DeviceMatrix:
+    def _slots(self):
+        i = np.ascontiguousarray(self.i, np.int32)
+        p = np.ascontiguousarray(self.p, np.int32)
+        x = np.ascontiguousarray(self.x, np.float64)
+        if p.shape[0] != self.cols() + 1 or i.shape[0] != x.shape[0]:
+            raise SparseB200Error(_lib.E_STRUCTURE, "slot lengths inconsistent with Dim")
+        return i, p, x
+
+    def _lease(self, multi: bool):
+        """The device handle for one call (a ShardedHostMatrix when the op has a several-GPU form and gpus > 1):
+        uploaded from the slots as they are now unless this Matrix is resident and its members were not re-pointed."""
+        src = (id(self.x), id(self.i), id(self.p), int(self.Dim[0]), int(self.Dim[1]))
+        if not self._resident or src != self._src:
+            self.release()
+        self._src = src
+        if multi and self._gpus > 1:
+            if self._sharded is None:
+                i, p, x = self._slots()
+                self._sharded = ShardedHostMatrix(i, p, x, self.rows(), self.cols(), self._gpus)
+            return self._sharded
         if self._dev is None:
-            i = np.ascontiguousarray(self.i, np.int32)
-            p = np.ascontiguousarray(self.p, np.int32)
-            x = np.ascontiguousarray(self.x, np.float64)
-            if p.shape[0] != self.cols() + 1 or i.shape[0] != x.shape[0]:
-                raise SparseB200Error(_lib.E_STRUCTURE, "slot lengths inconsistent with Dim")
+            i, p, x = self._slots()
             self._dev = DeviceMatrix.from_host(i, p, x, self.rows(), self.cols(), self._device, self._pin)
         return self._dev
 
+    def _call(self, multi: bool, fn):
+        try:
+            return fn(self._lease(multi))
+        finally:
+            if not self._resident:
+                self.release()
+
+    def _mirror(self) -> DeviceMatrix:
+        """The single-GPU mirror of a RESIDENT matrix (tests and tools that drive the device layer directly)."""
+        self._resident = True
+        return self._lease(False)
+
+    def resident(self, on: bool = True) -> "Matrix":
+        self._resident = bool(on)
+        if not on:
+            self.release()
+        return self
+
     def refresh(self) -> None:
-        """Re-upload x after an in-place change of the aliased host array."""
+        """Re-upload x into a resident mirror after an in-place change of the aliased host array (a no-op otherwise:
+        non-resident calls read x live)."""
+        x = np.ascontiguousarray(self.x, np.float64)
         if self._dev is not None:
-            self._dev.refresh_values(np.ascontiguousarray(self.x, np.float64))
+            self._dev.refresh_values(x)
+        if self._sharded is not None:
+            b = self._sharded.bounds()
+            for k in range(self._sharded.n_gpus):
+                self._sharded.block(k).refresh_values(x[int(self.p[b[k]]):])
 
     def release(self) -> None:
         if self._dev is not None:
             self._dev.close()
             self._dev = None
+        if self._sharded is not None:
+            self._sharded.close()
+            self._sharded = None
 
     # ---- the sweeps, RcppSparse.h:131-156 -----------------------------------------------------------------------------
     def colSums(self):
-        return self._mirror().col_sums()
+        return self._call(True, lambda m: m.col_sums())
 
     def rowSums(self):
-        return self._mirror().row_sums()
+        return self._call(True, lambda m: m.row_sums())
 
     def colMeans(self):
-        return self._mirror().col_means()
+        return self._call(True, lambda m: m.col_means())
 
     def rowMeans(self):
-        return self._mirror().row_means()
+        return self._call(True, lambda m: m.row_means())
 
     def crossprod(self):
-        return self._mirror().crossprod()
+        return self._call(False, lambda m: m.crossprod())
 
     # ---- A v and A^T v: additions (the reference has only the iterator idiom, SURVEY.md D1) -----------------------------
     def spmv(self, v):
-        return self._mirror().spmv(v)
+        return self._call(True, lambda m: m.spmv(v))
 
     def spmv_t(self, v):
-        return self._mirror().spmv_t(v)
+        return self._call(True, lambda m: m.spmv_t(v))
 
     # ---- RcppSparse.h:375-385 ---------------------------------------------------------------------------------------------
     def transpose(self) -> "Matrix":
-        ti, tp, tx = self._mirror().transpose_host()
+        ti, tp, tx = self._call(False, lambda m: m.transpose_host())
         return Matrix(tx, ti, tp, np.array([self.cols(), self.rows()], np.int32), self._device, self._pin)
 
     t = transpose  # the vignette lists .t() (Documentation.Rmd:250); the header defines transpose()

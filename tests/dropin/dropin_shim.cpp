@@ -100,16 +100,23 @@ int dropin_transpose(const int* i, const int* p, const double* x, int nrow, int 
     if (back.x.size() != T.x.size() || back.rows() != T.rows()) throw std::runtime_error("wrap/as round trip");
   });
 }
-// copies share one mirror; clone() does not; in-place edits need refresh()
+// The reference reads x live on every call: an in-place edit is seen by the next call without any refresh.  A
+// resident Matrix keeps its mirror (copies share it; clone() does not) and needs refresh() after an in-place edit.
 int dropin_alias_semantics(const int* i, const int* p, double* x, int nrow, int ncol, int64_t nnz, double* before,
-                           double* after) {
+                           double* after, double* stale, double* refreshed) {
   return guarded([&] {
     RcppSparse::Matrix A = view(i, p, x, nrow, ncol, nnz);
-    RcppSparse::Matrix B = A;  // aliases the same vectors and the same device mirror
+    RcppSparse::Matrix B = A;  // aliases the same vectors and the same device state
     out(B.colSums(), before);
     x[0] += 1000.0;
+    out(B.colSums(), after);  // live read, like the reference's loop over the R vector
+    A.resident();
+    if (!B.is_resident()) throw std::runtime_error("copies share the device state");
+    out(A.colSums(), after);
+    x[0] += 1000.0;
+    out(B.colSums(), stale);  // resident: the mirror still holds the old value
     A.refresh();
-    out(B.colSums(), after);
+    out(B.colSums(), refreshed);
   });
 }
 // public members may be re-pointed after construction (vignette: "m2.x = x; m2.i = i; ..."): the mirror follows

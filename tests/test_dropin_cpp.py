@@ -33,7 +33,7 @@ def shim():
     L.dropin_row_cursor.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, C.c_int, _i32, _f64, _ip, _ip]
     L.dropin_crossprod.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _f64]
     L.dropin_transpose.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _i32, _i32, _f64, _i32]
-    L.dropin_alias_semantics.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _f64, _f64]
+    L.dropin_alias_semantics.argtypes = [_i32, _i32, _f64, C.c_int, C.c_int, C.c_int64, _f64, _f64, _f64, _f64]
     L.dropin_repointed_members.argtypes = [_i32, _i32, _f64, _f64, C.c_int, C.c_int, C.c_int64, _f64, _f64]
     return L
 
@@ -90,12 +90,38 @@ def test_dropin_class_matches_golden(shim, golden):
 
 
 @pytest.mark.gpu
-def test_dropin_copies_share_the_mirror_and_refresh(shim):
+def test_dropin_reads_live_by_default_and_resident_mirrors_need_refresh(shim):
+    """The reference's methods loop over the R vectors on every call (RcppSparse.h:131-156) and the vignette edits
+    them in place (Documentation.Rmd:325-347): by default an edit is seen by the next call.  A resident Matrix keeps
+    its device mirror (shared by copies) and sees the edit after refresh()."""
     i, p = np.array([0, 1, 0], np.int32), np.array([0, 2, 3], np.int32)
     x = np.array([1.0, 2.0, 3.0])
-    before, after = np.empty(2), np.empty(2)
-    assert shim.dropin_alias_semantics(i, p, x, 2, 2, 3, before, after) == 0, shim.dropin_last_error()
+    before, after, stale, refreshed = np.empty(2), np.empty(2), np.empty(2), np.empty(2)
+    assert shim.dropin_alias_semantics(i, p, x, 2, 2, 3, before, after, stale, refreshed) == 0, shim.dropin_last_error()
     assert before.tolist() == [3.0, 3.0] and after.tolist() == [1003.0, 3.0]
+    assert stale.tolist() == [1003.0, 3.0] and refreshed.tolist() == [2003.0, 3.0]
+
+
+@pytest.mark.gpu
+def test_dropin_header_on_two_gpus(shim, monkeypatch):
+    """SB200_GPUS=2: the same user code, the sweeps behind sb200_sharded_* on two GPUs of this process."""
+    from rcppsparse_b200 import _lib, synth
+
+    if _lib.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("SB200_GPUS", "2")
+    spec = synth.config("C3", 0.002)
+    i, p, x = synth.generate_host(spec)
+    args = (i, p, x, spec.nrow, spec.ncol)
+    chk = oracle.best()
+    for op, name in ((1, "colSums"), (2, "rowSums"), (3, "colMeans"), (4, "rowMeans")):
+        out = np.empty(spec.ncol if op in (1, 3) else spec.nrow)
+        assert shim.dropin_reduce(op, i, p, x, spec.nrow, spec.ncol, x.shape[0], out) == 0, shim.dropin_last_error()
+        oracle.assert_within(name, out, getattr(chk, name)(*args), *args)
+    v = synth.dense_vector(3, spec.ncol)
+    y = np.empty(spec.nrow)
+    assert shim.dropin_spmv(0, i, p, x, spec.nrow, spec.ncol, x.shape[0], v, y) == 0, shim.dropin_last_error()
+    oracle.assert_within("spmv", y, chk.spmv(*args, v), *args, v=v)
 
 
 @pytest.mark.gpu
