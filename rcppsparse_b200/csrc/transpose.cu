@@ -11,7 +11,7 @@
 // Placement (transpose_place_kernel).  A CTA owns (row band, column split) units, handed out through an atomic
 // counter, heaviest work first come first served.  Its output rows are its own, so the only ordering problem is
 // inside the CTA: entries of one output row must appear in source-column order.  The CTA walks its columns in
-// chunks; one chunk's runs, concatenated in column order, are at most E = 4096 entries ("flat" order = final order
+// chunks; one chunk's runs, concatenated in column order, are placed at most E = 2048 entries at a time ("flat" order = final order
 // inside every row).  Per chunk:
 //   1. every lane expands its own runs into the flat list (entry index, column) — one shared-memory store per
 //      entry, no per-entry search;
@@ -73,7 +73,7 @@ __device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src_gmem)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int THREADS, int E>
-__global__ void __launch_bounds__(THREADS, (THREADS * 22 <= 3072 && E <= 2048) ? 4 : ((E <= 2048) ? 3 : 2)) transpose_place_kernel(const PlaceArgs a) {
+__global__ void __launch_bounds__(THREADS, (E <= 2048) ? 3 : 2) transpose_place_kernel(const PlaceArgs a) {
   constexpr int W = THREADS / 32;
   constexpr int U = 4;
   extern __shared__ __align__(16) unsigned char psm[];
@@ -307,7 +307,7 @@ int launch_place(sb200_matrix* m, const BandPlan* bp, int32_t* d_i_out, double* 
     if (v >= 1 && v <= PL_KMAX) K = v;
   }
   a.kcols = K;
-  a.prefetch = getenv("SB200_TRANSPOSE_NOPF") ? 0 : 1;
+  a.prefetch = getenv("SB200_TRANSPOSE_PF") ? 1 : 0;  // measured: the L2 prefetch of the next chunk's runs costs more than it hides
   // the unit counter lives in the handle's workspace, behind the lockstep counters
   a.unit_counter = reinterpret_cast<unsigned int*>(static_cast<unsigned char*>(m->d_ws) + 16 + 4 * 1024 + 8 * 1024 + 2048);
   SB_CUDA(cudaMemsetAsync(a.unit_counter, 0, sizeof(unsigned int), m->stream));
@@ -412,12 +412,10 @@ int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double
     const char* cfg = getenv("SB200_TRANSPOSE_CFG");
     if (cfg && !strcmp(cfg, "512x3072"))
       rc = launch_place<512, 3072>(m, bp, d_i_out, d_x_out);
-    else if (cfg && !strcmp(cfg, "128x2048"))
-      rc = launch_place<128, 2048>(m, bp, d_i_out, d_x_out);
-    else if (cfg && !strcmp(cfg, "256x2048"))
-      rc = launch_place<256, 2048>(m, bp, d_i_out, d_x_out);
-    else
+    else if (cfg && !strcmp(cfg, "256x4096"))
       rc = launch_place<256, 4096>(m, bp, d_i_out, d_x_out);
+    else  // measured at C3 (profiles/r02): 256x2048 (3 CTAs/SM) 26.5-27.8 ms, 256x4096 (2) 28.3-29.1, 128x2048 (4) 31.1, 512x3072 29.4
+      rc = launch_place<256, 2048>(m, bp, d_i_out, d_x_out);
   } else {
     rc = launch_transpose_banded(m, bp, d_i_out, d_x_out);
   }

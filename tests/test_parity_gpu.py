@@ -139,7 +139,7 @@ def test_synth_transpose_bit_exact(synth_case, checker):
     A.release()
 
 
-@pytest.mark.parametrize("cfg", ["256x4096:1", "256x4096:4", "512x3072:2"])
+@pytest.mark.parametrize("cfg", ["256x2048:1", "256x2048:3", "256x4096:4", "512x3072:2"])
 def test_transpose_chunk_sort_placement_on_every_shape(synth_case, cfg, monkeypatch, checker):
     """The chunk-sorting placement kernel (transpose.cu) forced on every synthetic shape — also the tall ones the
     library would give to the banded two-pass kernel — in both block geometries and with 1, 2 and 4 columns per
@@ -493,26 +493,32 @@ def test_band_companion_products_on_synthetic_shapes(case, band_rows, monkeypatc
         oracle.assert_within("rowSums", D.row_sums(), checker.rowSums(*args), *args, tol=TOL)
 
 
-@pytest.mark.parametrize("cap", ["8", "16"])
-@pytest.mark.parametrize("ring", ["1024,2", "640,3", "512,4"])
-@pytest.mark.parametrize("regime", ["const_0_1_2", "const_10", "const_100", "const_938_939_940", "long_then_dust", "sawtooth"])
-def test_band_companion_piece_sizes_rings_and_run_lengths(regime, ring, cap, monkeypatch, checker):
-    """Both piece sizes (entries a thread sums; normally picked from the mean run length) and every instantiated
-    ring geometry of the band sweep on every run-length regime, with 1 band and with 24 bands of 256 rows."""
+@pytest.mark.parametrize("block", ["4", "8"])
+@pytest.mark.parametrize("regime", ["const_0_1_2", "const_3", "const_10", "const_100", "const_938_939_940", "long_then_dust", "sawtooth"])
+def test_band_companion_block_sizes_and_run_lengths(regime, block, monkeypatch, checker):
+    """Both block sizes of the band-major layout (entries a thread sums per block; runs are padded to whole blocks with
+    entries that point at a dummy 0.0 slot) on every run-length regime, with 1 band and with 24 bands of 256 rows; an
+    operand full of NaN / Inf outside the touched rows must not leak through the padding."""
     lengths = LENGTH_REGIMES[regime]
     nrow = 6000
     i, p, x = _columns_of_lengths(lengths, nrow, zlib_seed(regime) + 5)
     args = (i, p, x, nrow, len(lengths))
     v_row = synth.dense_vector(11, nrow)
     want = checker.spmv_t(*args, v_row)
-    monkeypatch.setenv("SB200_BS_CAP", cap)
-    monkeypatch.setenv("SB200_BS_CFG", ring)
+    monkeypatch.setenv("SB200_BS_BLOCK", block)
     for rows in (None, "256"):
         if rows:
             monkeypatch.setenv("SB200_BMC_ROWS", rows)
         with DeviceMatrix.from_host(*args) as D:
             D.band_companion(0, 1)
             oracle.assert_within("spmv_t", D.spmv_t(v_row), want, *args, v=v_row, tol=TOL)
+            # rows no entry touches may hold anything: padding entries never read them (they read the dummy slot)
+            v_bad = v_row.copy()
+            untouched = np.setdiff1d(np.arange(nrow), i)
+            v_bad[untouched[::2]] = np.nan
+            v_bad[untouched[1::2]] = np.inf
+            v_bad[0] = v_row[0] if 0 in i else np.nan
+            oracle.assert_within("spmv_t", D.spmv_t(v_bad), checker.spmv_t(*args, v_bad), *args, v=np.where(np.isfinite(v_bad), v_bad, 0.0), tol=TOL)
 
 
 def test_band_companion_golden_edges(golden, checker):
