@@ -150,6 +150,8 @@ int sb200_matrix_band_companion(sb200_matrix* m, int which, int action);
 /* Bit mask of the cached layouts this mirror holds: 1 row-ordered copy, 2 band-major companion (A^T v),
  * 4 band-major companion of the row-ordered copy (A v), 8 transpose plan. */
 int sb200_matrix_layouts(sb200_matrix* m, int* mask);
+/* HBM bytes the cached layouts of this mirror occupy (row-ordered copy + band-major companions), beside its i/p/x. */
+int sb200_matrix_layout_bytes(sb200_matrix* m, int64_t* bytes);
 
 /* ---- cross-GPU exchange for column-sharded matrices (one process per GPU, GPUs of one node) ---------
  * The reference is single-process; a column-sharded deployment needs two exchange steps:
@@ -179,6 +181,19 @@ int sb200_exchange_barrier(sb200_exchange* x, void* cuda_stream);
  * from a peer for SB200_EXCHANGE_TIMEOUT_S seconds (default 600) raises the window's error word and traps its kernel: the
  * stream and every later CUDA call fail, no result computed from partial data is ever returned. */
 int sb200_exchange_status(sb200_exchange* x);
+
+/* ---- range cursors and dense extraction as batched device ops ----------------------------------
+ * sb200_col_sums_in_rows: for every column c at once, out[c] = the sum a user loop over
+ * InnerIteratorInRange(A, c, s) (negate = 0, reference RcppSparse.h:238-264) or InnerIteratorNotInRange(A, c, s)
+ * (negate = 1, :270-321) accumulates: the entries of column c whose row is / is not in the index set rows[n] (host
+ * array; order and duplicates do not matter; indices outside [0, nrow) select nothing).  Entries outside the
+ * selection are skipped, not multiplied by zero: an Inf or NaN outside it does not reach the sum.
+ * sb200_gather_block: out[jc * nr + ir] = A(rows[ir], cols[jc]), dense column-major nr x nc (reference :76-92
+ * operator()(IntegerVector, IntegerVector)); rows = NULL takes every row (:95-107 col(...)), cols = NULL every column
+ * (:110-128 row(...)); indices outside the matrix give 0. */
+int sb200_col_sums_in_rows(sb200_matrix* m, const int32_t* rows, int64_t n, int negate, double* out /* ncol */);
+int sb200_gather_block(sb200_matrix* m, const int32_t* rows, int64_t nr, const int32_t* cols, int64_t nc,
+                       double* out /* nr * nc, column-major, host */);
 
 /* ---- one process, several GPUs (SURVEY.md 8e behind the shim) --------------------------------------------------
  * The reference is ONE R process calling Matrix methods (RcppSparse.h:131-156); a drop-in cannot be launched as one

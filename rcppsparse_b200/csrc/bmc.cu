@@ -459,6 +459,12 @@ int build_band_companion(sb200_matrix* m) {
   return SB200_OK;
 }
 
+int64_t band_companion_bytes(const sb200_matrix* m) {
+  const BandCompanion* bc = m->bmc;
+  if (!bc) return 0;
+  return bc->entries_padded * 10 + (bc->entries_padded / bc->B) * 4 + static_cast<int64_t>(bc->nb + 1) * 8;
+}
+
 int launch_bandsweep(sb200_matrix* m, const double* d_v, double* d_out) {
   const BandCompanion* bc = m->bmc;
   if (!bc) return fail(SB200_E_INVALID, "no band-major companion on this mirror");

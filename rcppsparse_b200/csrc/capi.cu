@@ -712,6 +712,18 @@ int sb200_matrix_layouts(sb200_matrix* m, int* mask) {
   return SB200_OK;
 }
 
+int sb200_matrix_layout_bytes(sb200_matrix* m, int64_t* bytes) {
+  ENTER(m);
+  if (!bytes) return fail(SB200_E_INVALID, "bytes is NULL");
+  int64_t total = band_companion_bytes(m);
+  if (m->rows_state == 1 && m->rows) {
+    total += 12 * m->rows->nnz + 4 * (static_cast<int64_t>(m->rows->ncol) + 1);  // row-ordered copy: x', i', p'
+    total += band_companion_bytes(m->rows);
+  }
+  *bytes = total;
+  return SB200_OK;
+}
+
 int sb200_algorithmic_bytes(const sb200_matrix* m, const char* op, int64_t* bytes) {
   SB_TRY(check_handle(m));
   if (!op || !bytes) return fail(SB200_E_INVALID, "NULL argument");

@@ -151,6 +151,7 @@ int launch_band_ptr(sb200_matrix* m, const int32_t* d_rb, int nb, int32_t* d_bpt
 int build_band_companion(sb200_matrix* m);  // non-fatal: leaves bmc_state = -1 when it cannot be built
 void drop_band_companion(sb200_matrix* m, cudaStream_t s);
 int launch_bandsweep(sb200_matrix* m, const double* d_v, double* d_out);  // y[ncol] = A^T v from the companion
+int64_t band_companion_bytes(const sb200_matrix* m);                    // HBM the companion occupies (0 without one)
 void free_matrix_plans(sb200_matrix* m, cudaStream_t s);
 // hostcopy.cu: pageable host memory through worker threads with pinned chunks (blocking)
 bool host_is_pageable(const void* p);

@@ -77,6 +77,7 @@ struct SweepParams {
   int32_t* carry_col;  // [grid]
   double* carry_val;   // [grid]
   unsigned int* ticket;
+  int mask;  // SPMV_T only: v is an indicator — entries whose v[row] is 0 are SKIPPED (x * 0 would turn Inf into NaN)
 };
 
 struct StageMeta {
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK) sweep_kernel(const SweepParams pr
 #pragma unroll
       for (int r = 0; r < IPT; ++r) {
         const int k = tid + r * THREADS;
-        if (k < mt.nk) xw[k] = __dmul_rn(xw[k], g[r]);
+        if (k < mt.nk) xw[k] = prm.mask ? (g[r] != 0.0 ? xw[k] : 0.0) : __dmul_rn(xw[k], g[r]);
       }
       consumer_sync();
     }
@@ -610,6 +611,33 @@ int launch_vec_div(cudaStream_t s, double* d, int64_t n, double divisor) {
   return SB200_OK;
 }
 
+static int launch_tile_sweep(sb200_matrix* m, SweepMode mode, const double* d_v, double* d_out, int mask) {
+  if (m->n_tiles == 0) return SB200_OK;  // ncol == 0 and nnz == 0: nothing to produce
+  SweepParams prm;
+  prm.i = m->d_i;
+  prm.p = m->d_p;
+  prm.x = m->d_x;
+  prm.plan = (mode == SWEEP_COLSUM) ? m->d_plan : m->d_plan_g;
+  prm.n_tiles = (mode == SWEEP_COLSUM) ? m->n_tiles : m->n_tiles_g;
+  prm.ncol = m->ncol;
+  prm.nnz = static_cast<int32_t>(m->nnz);
+  prm.v = d_v;
+  prm.out = d_out;
+  prm.mask = mask;
+  // workspace layout: [ticket u32 | pad to 16] [carry_col int32 x 1024] [carry_val f64 x 1024]
+  unsigned char* ws = static_cast<unsigned char*>(m->d_ws);
+  prm.ticket = reinterpret_cast<unsigned int*>(ws);
+  prm.carry_col = reinterpret_cast<int32_t*>(ws + 16);
+  prm.carry_val = reinterpret_cast<double*>(ws + 16 + 4 * 1024);
+  const SweepConfig cfg = sweep_config(mode);
+  switch (mode) {
+    case SWEEP_COLSUM: return launch_sweep_m<SWEEP_COLSUM>(m, prm, cfg);
+    case SWEEP_SPMV_T: return launch_sweep_m<SWEEP_SPMV_T>(m, prm, cfg);
+    case SWEEP_SPMV: return launch_sweep_m<SWEEP_SPMV>(m, prm, cfg);
+    default: return fail(SB200_E_INVALID, "unknown sweep mode");
+  }
+}
+
 int launch_sweep(sb200_matrix* m, SweepMode mode, const double* d_v, double divisor, double* d_out) {
   if ((mode == SWEEP_ROWSUM || mode == SWEEP_SPMV) && m->nnz > 0 && m->nrow > 0) {
     // A mirror whose row-indexed sweeps keep being asked for gets a row-major copy of itself: from then on a
@@ -676,36 +704,16 @@ int launch_sweep(sb200_matrix* m, SweepMode mode, const double* d_v, double divi
     if (divisor != 0.0) SB_TRY(launch_vec_div(m->stream, d_out, m->nrow, divisor));
     return SB200_OK;
   }
-  if (m->n_tiles == 0) return SB200_OK;  // ncol == 0 and nnz == 0: nothing to produce
-
-  SweepParams prm;
-  prm.i = m->d_i;
-  prm.p = m->d_p;
-  prm.x = m->d_x;
-  prm.plan = (mode == SWEEP_COLSUM) ? m->d_plan : m->d_plan_g;
-  prm.n_tiles = (mode == SWEEP_COLSUM) ? m->n_tiles : m->n_tiles_g;
-  prm.ncol = m->ncol;
-  prm.nnz = static_cast<int32_t>(m->nnz);
-  prm.v = d_v;
-  prm.out = d_out;
-  // workspace layout: [ticket u32 | pad to 16] [carry_col int32 x 1024] [carry_val f64 x 1024]
-  unsigned char* ws = static_cast<unsigned char*>(m->d_ws);
-  prm.ticket = reinterpret_cast<unsigned int*>(ws);
-  prm.carry_col = reinterpret_cast<int32_t*>(ws + 16);
-  prm.carry_val = reinterpret_cast<double*>(ws + 16 + 4 * 1024);
-  const SweepConfig cfg = sweep_config(mode);
-  int rc;
-  switch (mode) {
-    case SWEEP_COLSUM: rc = launch_sweep_m<SWEEP_COLSUM>(m, prm, cfg); break;
-    case SWEEP_SPMV_T: rc = launch_sweep_m<SWEEP_SPMV_T>(m, prm, cfg); break;
-    case SWEEP_SPMV: rc = launch_sweep_m<SWEEP_SPMV>(m, prm, cfg); break;
-    default: return fail(SB200_E_INVALID, "unknown sweep mode");
-  }
-  SB_TRY(rc);
+  SB_TRY(launch_tile_sweep(m, mode, d_v, d_out, 0));
   // colMeans: sums[c] / Dim[0] as a second pass over the ncol outputs, exactly the reference's
   // structure (RcppSparse.h:146-148); 16 B per column next to 8 B per stored entry.
   if (mode == SWEEP_COLSUM && divisor != 0.0) SB_TRY(launch_vec_div(m->stream, d_out, m->ncol, divisor));
   return SB200_OK;
 }
+
+// Masked column sums (N4): out[c] = sum of the entries of column c whose row has d_mask[row] != 0 — the sweep a user
+// writes with InnerIteratorInRange / InnerIteratorNotInRange (reference RcppSparse.h:238-321), all columns at once.
+// Always the tile sweep on the CSC arrays: skipping an entry is not the same as multiplying it by 0.0.
+int launch_masked_col_sums(sb200_matrix* m, const double* d_mask, double* d_out) { return launch_tile_sweep(m, SWEEP_SPMV_T, d_mask, d_out, 1); }
 
 }  // namespace sb200

@@ -146,6 +146,12 @@ class DeviceMatrix:
         check(_lib.lib().sb200_matrix_layouts(self._h, C.byref(m)))
         return m.value
 
+    def layout_bytes(self) -> int:
+        """HBM the cached layouts occupy beside i/p/x (row-ordered copy + band-major companions)."""
+        n = C.c_int64()
+        check(_lib.lib().sb200_matrix_layout_bytes(self._h, C.byref(n)))
+        return n.value
+
     def refresh_values(self, x) -> None:
         check(_lib.lib().sb200_matrix_refresh_values(self._h, _ptr(x)))
 
@@ -207,6 +213,26 @@ class DeviceMatrix:
         y = np.empty(self.ncol, np.float64)
         check(_lib.lib().sb200_spmv_t(self._h, _ptr(v), _ptr(y)))
         return y
+
+    # ---- range cursors and dense extraction as batched device ops --------------------------------
+    def col_sums_in_rows(self, rows, negate: bool = False):
+        """Per column, the sum over the entries whose row is (negate: is not) in ``rows`` — every column's
+        InnerIteratorInRange / InnerIteratorNotInRange sweep at once (reference RcppSparse.h:238-321)."""
+        rows = np.ascontiguousarray(rows, np.int32)
+        out = np.empty(self.ncol, np.float64)
+        check(_lib.lib().sb200_col_sums_in_rows(self._h, _ptr(rows), int(rows.shape[0]), 1 if negate else 0, _ptr(out)))
+        return out
+
+    def gather_block(self, rows=None, cols=None):
+        """Dense A[rows, cols] (reference :76-128 operator()(IntegerVector, IntegerVector), col(...), row(...));
+        None = every row / column."""
+        r = None if rows is None else np.ascontiguousarray(rows, np.int32)
+        c = None if cols is None else np.ascontiguousarray(cols, np.int32)
+        nr = self.nrow if r is None else int(r.shape[0])
+        nc = self.ncol if c is None else int(c.shape[0])
+        out = np.empty((nc, nr), np.float64)  # column-major nr x nc
+        check(_lib.lib().sb200_gather_block(self._h, _ptr(r), nr, _ptr(c), nc, _ptr(out)))
+        return out.T
 
     def transpose_host(self):
         p = np.empty(self.nrow + 1, np.int32)

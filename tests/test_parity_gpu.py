@@ -139,14 +139,16 @@ def test_synth_transpose_bit_exact(synth_case, checker):
     A.release()
 
 
+@pytest.mark.parametrize("rank", ["bitmap", "match"])
 @pytest.mark.parametrize("cfg", ["256x2048:1", "256x2048:3", "256x4096:4", "512x3072:2"])
-def test_transpose_chunk_sort_placement_on_every_shape(synth_case, cfg, monkeypatch, checker):
+def test_transpose_chunk_sort_placement_on_every_shape(synth_case, cfg, rank, monkeypatch, checker):
     """The chunk-sorting placement kernel (transpose.cu) forced on every synthetic shape — also the tall ones the
     library would give to the banded two-pass kernel — in both block geometries and with 1, 2 and 4 columns per
     thread and chunk: bit-exact whatever the geometry."""
     name, spec, i, p, x = synth_case
     geom, kcols = cfg.split(":")
     monkeypatch.setenv("SB200_TRANSPOSE_PATH", "place")
+    monkeypatch.setenv("SB200_TRANSPOSE_RANK", rank)  # bitmap ranks (default) or per-warp counters + match.any
     monkeypatch.setenv("SB200_TRANSPOSE_CFG", geom)
     monkeypatch.setenv("SB200_TRANSPOSE_KCOLS", kcols)
     with DeviceMatrix.from_host(i, p, x, spec.nrow, spec.ncol) as D:
@@ -167,7 +169,9 @@ def test_transpose_chunks_larger_than_the_image(bands, kcols, monkeypatch, check
     want = checker.transpose(i, p, x, spec.nrow, spec.ncol)
     monkeypatch.setenv("SB200_TRANSPOSE_BANDS", bands)
     monkeypatch.setenv("SB200_TRANSPOSE_KCOLS", kcols)
-    for path in ("place", "banded"):
+    for path in ("place", "place-match", "banded"):
+        monkeypatch.setenv("SB200_TRANSPOSE_RANK", "match" if path == "place-match" else "bitmap")
+        path = "place" if path.startswith("place") else path
         monkeypatch.setenv("SB200_TRANSPOSE_PATH", path)
         with DeviceMatrix.from_host(i, p, x, spec.nrow, spec.ncol) as D:
             ti, tp, tx = D.transpose_host()
