@@ -10,8 +10,8 @@ HBM by the integer-exact recipe of rcppsparse_b200/synth.py.  One STEP = one pas
 config names — colSums, rowSums, colMeans, rowMeans (reference RcppSparse.h:131-156) — over the device-resident
 matrix; value = 4 * nnz / step time.  At N > 1 (torchrun, one rank per GPU) every rank owns a C2-sized column
 block (weak scaling); column results are assembled and row results summed by the library's exchange kernels
-over NVLink peer memory, each op's exchange running beside the next op's sweep, every result waited for before
-its step ends.
+over NVLink peer memory, each op's exchange running beside the next op's sweep (the last op's beside the first
+sweep of the next step); every result of every timed step is complete before the closing barrier.
 
 The other three hot ops run on THEIR OWN BASELINE configs in the same run and are reported in
 `roofline_by_op` next to the C2 reductions (same K/W, CUDA events on the launching stream, inputs >> L2):
@@ -416,7 +416,7 @@ def section_transpose(ctx, args, peak, steps, warmup):
     scale = float(b.abs().max().item()) or 1.0
     drift = float((a - b).abs().max().item()) / scale
     ab = D.algorithmic_bytes("transpose")
-    entry = roofline_entry("transpose", "C3", "transpose_place_kernel", ab, ms, peak, D.nnz,
+    entry = roofline_entry("transpose", "C3", "transpose_bitrank_kernel", ab, ms, peak, D.nnz,
                            {"ms_min": ms_min, "first_call_ms": first_ms, "nnz": D.nnz,
                             "what": "sb200_transpose_dev: allocation of the result from the pool + (cached) band plan + placement kernel + "
                                     "the result's tile plans; first_call_ms includes building the band plan",
@@ -640,18 +640,25 @@ def run_b200(args, ops):
             return None
         return getattr(S, op)(async_op=overlap)
 
-    def run_step(marks=None):
+    def wait_all(pend):
+        for r in pend or ():
+            if r is not None:
+                r.wait()
+
+    def run_step(marks=None, prev=None):
+        """One step.  With overlapped exchanges the results of the PREVIOUS step are waited for after this step's
+        first sweep has been launched (its last exchange then runs beside that sweep instead of ending the step
+        alone); the caller waits for the last step's results before the closing barrier.  Returns what is pending."""
         pend = []
         for k, op in enumerate(ops):
             pend.append(run_op(op))
+            if k == 0:
+                wait_all(prev)
             if marks is not None:
                 marks[k + 1].record()
-        if overlap:
-            for r in pend:
-                if r is not None:
-                    r.wait()
         if marks is not None:
             marks[len(ops) + 1].record()
+        return pend if overlap else None
 
     # ---- row sums of a resident mirror -------------------------------------------------------------------------
     # The library serves rowSums/rowMeans with its scatter kernel until a mirror has been asked for them more than
@@ -697,8 +704,11 @@ def run_b200(args, ops):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    pend = None
     for _ in range(max(args.warmup, 3)):
-        run_step()
+        pend = run_step(prev=pend)
+    wait_all(pend)
+    pend = None
     barrier()
     if rank == 0:
         sampler.wait_first_sample()
@@ -709,14 +719,17 @@ def run_b200(args, ops):
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
         ev[s][0].record()
-        run_step(ev[s])
+        pend = run_step(ev[s], prev=pend)
+    wait_all(pend)  # every result of every timed step is complete before the closing barrier
+    tail_ev = torch.cuda.Event(enable_timing=True)
+    tail_ev.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     sampler.mark_end()
     launches = _lib.lib().sb200_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
-    total_ms = ev[0][0].elapsed_time(ev[-1][-1])  # device time of exactly K steps on the launching stream
+    total_ms = ev[0][0].elapsed_time(tail_ev)  # device time of exactly K steps on the launching stream, last results included
     per_op_ms = {op: float(np.mean([ev[s][k].elapsed_time(ev[s][k + 1]) for s in range(args.steps)]))
                  for k, op in enumerate(ops)}
     per_op_min = {op: float(np.min([ev[s][k].elapsed_time(ev[s][k + 1]) for s in range(args.steps)]))
@@ -785,7 +798,7 @@ def run_b200(args, ops):
                   "band_scatter_kernel" if row_path_final == "banded" else "rowsum_stream_kernel")
     kernel_of = {"rowSums": row_kernel, "rowMeans": row_kernel, "colSums": "sweep_kernel<COLSUM>",
                  "colMeans": "sweep_kernel<COLSUM>", "spmv": "sweep_kernel<SPMV>", "spmv_t": "sweep_kernel<SPMV_T>",
-                 "transpose": "transpose_place_kernel"}
+                 "transpose": "transpose_bitrank_kernel"}
     wl = args.workload.upper()
     for op in ops:
         ab = ab_of[op]
@@ -829,7 +842,7 @@ def run_b200(args, ops):
         "exchange": (None if world == 1 else
                      "libsparse_b200 kernels over NVLink peer memory (cudaIpc window): P2P stores of each rank's slice for "
                      "column results, rank-ordered P2P reduction for row results, flag barriers; op k's exchange runs beside op k+1's "
-                     "sweep, every result is waited for before its step ends" if S.exchange == "p2p" else
+                     "sweep (the last op's beside the next step's first sweep), all results complete inside the timed region" if S.exchange == "p2p" else
                      "NCCL all-gather / all-reduce" + (", left in flight under the next op's sweep" if overlap else "")),
         "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall, "e2e": e2e,
     }

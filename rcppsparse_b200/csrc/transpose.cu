@@ -425,12 +425,17 @@ __global__ void __launch_bounds__(THREADS, (E <= 2048) ? 3 : 2) transpose_bitran
             ec[j] = flat_c[q];
           }
         }
+        const int used = static_cast<int>((n + THREADS - 1) / THREADS);  // slots per thread that hold anything (uniform)
 #pragma unroll
-        for (int j = 0; j < EPT; ++j)
+        for (int j = 0; j < EPT; ++j) {
+          if (j >= used) break;
           if (ek[j] >= 0) er[j] = ptx::ld_stream_s32(bv.i + ek[j]) - row0;
+        }
 #pragma unroll
-        for (int j = 0; j < EPT; ++j)
+        for (int j = 0; j < EPT; ++j) {
+          if (j >= used) break;
           if (ek[j] >= 0) atomicOr(&bm[er[j] * WW + (ec[j] >> 5)], 1u << (ec[j] & 31u));
+        }
         __syncthreads();
         // ---- layout: prefix popcounts per row, block scan over the rows, cursors ---------------------------------
         uint32_t tot[2] = {0u, 0u};
@@ -472,6 +477,7 @@ __global__ void __launch_bounds__(THREADS, (E <= 2048) ? 3 : 2) transpose_bitran
         // ---- place: rank = entries of my row in earlier columns of the chunk -----------------------------------------
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
+          if (j >= used) break;
           if (ek[j] >= 0) {
             const int wi = er[j] * WW + static_cast<int>(ec[j] >> 5);
             const uint32_t below = bm[wi] & ((1u << (ec[j] & 31u)) - 1u);
