@@ -264,6 +264,22 @@ unsigned long long exchange_timeout_ns() {
   return ns;
 }
 
+// CTAs of an exchange kernel: they run beside the next op's sweep, so they must leave it its SM slots.  Measured at
+// N = 2 (profiles/r02, C2 step of four sweeps): 296 CTAs 0.581 ms/step (the sweep beside a reduction takes 0.155 instead
+// of 0.134 ms), 148: 0.552, 74: 0.548, 32: 0.548 — half a CTA per SM is enough to move 8 MB over NVLink inside one
+// sweep.  SB200_XG_CTAS overrides.
+int exchange_max_ctas() {
+  static const int n = [] {
+    int v = 74;
+    if (const char* e = getenv("SB200_XG_CTAS")) {
+      const int w = atoi(e);
+      if (w >= 1 && w <= 1184) v = w;
+    }
+    return v;
+  }();
+  return n;
+}
+
 int launch_barrier(sb200_exchange* x, cudaStream_t st) {
   x->epoch += 1;
   xg_barrier_kernel<<<1, 32, 0, st>>>(x->peers, x->rank, x->world, x->epoch, exchange_timeout_ns());
@@ -418,7 +434,7 @@ int sb200_exchange_gather(sb200_exchange* x, void* cuda_stream, int64_t full_off
   }
   if (x->world > 1) {
     int64_t blocks = (slice_len + 255) / 256;
-    if (blocks > 296) blocks = 296;
+    if (blocks > exchange_max_ctas()) blocks = exchange_max_ctas();
     if (blocks < 1) blocks = 1;  // an empty slice still takes part in the barrier
     x->epoch += 1;
     xg_push_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x->peers, x->rank, x->world, off, slice_len, x->epoch, exchange_timeout_ns());
@@ -440,7 +456,7 @@ int sb200_exchange_reduce(sb200_exchange* x, void* cuda_stream, int64_t partial_
   auto cut = [&](int q) { return q >= x->world ? n : ((n * q / x->world) & ~static_cast<int64_t>(1)); };
   const int64_t r0 = cut(x->rank), r1 = cut(x->rank + 1);
   int64_t blocks = ((r1 - r0) / 4 + 255) / 256;
-  if (blocks > 296) blocks = 296;  // two CTAs per SM beside a running sweep; all co-resident (the gate relies on CTA 0 running)
+  if (blocks > exchange_max_ctas()) blocks = exchange_max_ctas();  // at most two CTAs per SM beside a running sweep
   if (blocks < 1) blocks = 1;
   const unsigned g = static_cast<unsigned>(blocks);
   const size_t po = static_cast<size_t>(partial_offset), ro = static_cast<size_t>(result_offset);

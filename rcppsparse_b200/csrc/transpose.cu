@@ -45,7 +45,8 @@ namespace sb200 {
 namespace {
 
 constexpr int PL_ROWS_CAP = 384;  // rows per band
-constexpr int PL_KMAX = 4;        // columns per thread and chunk, at most
+constexpr int PL_KMAX = 4;        // columns per thread and chunk, at most (counter / match.any kernel)
+constexpr int PB_KMAX = 2;        // same, bitmap-rank kernel (its bitmap has THREADS * K bits per row)
 
 struct PlaceArgs {
   BandView bv;
@@ -345,9 +346,9 @@ __global__ void __launch_bounds__(THREADS, (E <= 2048) ? 3 : 2) transpose_bitran
     if (R <= 0 || c_lo >= c_hi) continue;
     for (int r = tid; r < R; r += THREADS) cursor[r] = static_cast<uint32_t>(a.off[static_cast<int64_t>(row0 + r) * bv.S + h]);
 
-    int32_t ns[PL_KMAX], ne[PL_KMAX];
+    int32_t ns[PB_KMAX], ne[PB_KMAX];
 #pragma unroll
-    for (int kk = 0; kk < PL_KMAX; ++kk) {
+    for (int kk = 0; kk < PB_KMAX; ++kk) {
       ns[kk] = ne[kk] = 0;
       const int64_t c = static_cast<int64_t>(c_lo) + (warp * K + kk) * 32 + lane;
       if (kk < K && c < c_hi) {
@@ -356,11 +357,11 @@ __global__ void __launch_bounds__(THREADS, (E <= 2048) ? 3 : 2) transpose_bitran
       }
     }
     for (int64_t cbase = c_lo; cbase < c_hi; cbase += CC, ++chunk_no) {
-      int32_t rs[PL_KMAX], rl[PL_KMAX];
-      uint32_t ex[PL_KMAX];
+      int32_t rs[PB_KMAX], rl[PB_KMAX];
+      uint32_t ex[PB_KMAX];
       uint32_t wtot = 0;
 #pragma unroll
-      for (int kk = 0; kk < PL_KMAX; ++kk) {
+      for (int kk = 0; kk < PB_KMAX; ++kk) {
         rs[kk] = ns[kk];
         rl[kk] = ne[kk] - ns[kk];
         uint32_t incl = static_cast<uint32_t>(rl[kk]);
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(THREADS, (E <= 2048) ? 3 : 2) transpose_bitran
         wtot += __shfl_sync(0xffffffffu, incl, 31);
       }
 #pragma unroll
-      for (int kk = 0; kk < PL_KMAX; ++kk) {  // next chunk's descriptors
+      for (int kk = 0; kk < PB_KMAX; ++kk) {  // next chunk's descriptors
         ns[kk] = ne[kk] = 0;
         const int64_t c = cbase + CC + (warp * K + kk) * 32 + lane;
         if (kk < K && c < c_hi) {
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(THREADS, (E <= 2048) ? 3 : 2) transpose_bitran
         // ---- clear the bitmap of the rows in use; owner expansion of the flat slots [lo, hi) -----------------------
         for (int e = tid; e < R * WW; e += THREADS) bm[e] = 0u;
 #pragma unroll
-        for (int kk = 0; kk < PL_KMAX; ++kk) {
+        for (int kk = 0; kk < PB_KMAX; ++kk) {
           if (kk < K && rl[kk] > 0) {
             const uint32_t q0 = woff + ex[kk];
             const uint32_t q1 = q0 + static_cast<uint32_t>(rl[kk]);
@@ -620,9 +621,12 @@ int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double
   }
   const bool cached = m->plan_transpose != nullptr;
   if (!cached) {
-    int S = kind == 2 ? 4 : 2;
+    // chunk sort: many column splits — the units of one split run side by side (they are handed out in (split, band)
+    // order), so neighbouring bands read their neighbouring runs of the same columns while the shared 32-byte sectors are
+    // still in L2 (C3: 28.4 ms with 4 splits, 25.6 / 24.4 / 24.2 with 16 / 64 / 256)
+    int S = kind == 2 ? 64 : 2;
     int bands = kind == 2 ? 2 * m->sm_count : m->sm_count;
-    if (env_splits >= 1 && env_splits <= 64) S = env_splits;
+    if (env_splits >= 1 && env_splits <= 1024) S = env_splits;
     if (env_bands >= 1) bands = env_bands;
     BandPlan* bp = nullptr;
     SB_TRY(build_band_plan(m, kind == 2 ? PL_ROWS_CAP : 2432, bands, S, &bp));

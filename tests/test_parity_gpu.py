@@ -344,6 +344,31 @@ def test_view_aliases_host_memory_and_refresh():
     assert A.x[0] == 999.0  # clone() is a deep copy (RcppSparse.h:54-60)
 
 
+def test_reads_are_live_by_default_and_resident_mirrors_need_refresh():
+    """The reference's methods loop over the R vectors on every call (RcppSparse.h:131-156): an in-place edit is seen by the
+    next call with no refresh.  resident() keeps the device mirror (and the layouts cached on it): then refresh() is
+    what makes an edit visible, and re-pointing a member rebuilds the mirror."""
+    x = np.array([1.0, 2.0, 3.0])
+    i, p, dim = np.array([0, 1, 0], np.int32), np.array([0, 2, 3], np.int32), np.array([2, 2], np.int32)
+    A = Matrix(x, i, p, dim)
+    assert A.colSums().tolist() == [3.0, 3.0]
+    x[0] = 11.0
+    assert A.colSums().tolist() == [13.0, 3.0]       # live read
+    assert A._dev is None                            # nothing outlives the call
+    A.resident()
+    assert A.colSums().tolist() == [13.0, 3.0]
+    x[0] = 21.0
+    assert A.colSums().tolist() == [13.0, 3.0]       # the mirror still holds the old value
+    A.refresh()
+    assert A.colSums().tolist() == [23.0, 3.0]
+    A.x = np.array([1.0, 1.0, 1.0])                  # re-pointed member: new upload
+    assert A.colSums().tolist() == [2.0, 1.0]
+    for _ in range(10):                              # resident: the row sums move to the row-ordered copy after 8 calls
+        assert A.rowSums().tolist() == [2.0, 1.0]
+    assert A._mirror().row_path() == "row-companion"
+    A.release()
+
+
 def test_from_s4_and_exported_function_accept_scipy_csc():
     import scipy.sparse as sp
 
