@@ -176,6 +176,15 @@ int sb200_exchange_gather(sb200_exchange* x, void* cuda_stream, int64_t full_off
  * RcppSparse.h:154). partial and result must not overlap. */
 int sb200_exchange_reduce(sb200_exchange* x, void* cuda_stream, int64_t partial_offset, int64_t result_offset, int64_t n,
                           double divisor);
+/* Sharded transpose: every rank has transposed its own column block (d_p_loc[nrow+1], d_cols local column ids, d_vals);
+ * output row r belongs to the rank q with row_bounds[q] <= r < row_bounds[q+1] and is the concatenation, in rank order, of
+ * the ranks' segments of row r.  Writes MY segment of every row straight into its owner's window — column ids (made global
+ * with col_offset) at byte offset cols_offsets[q], values at vals_offsets[q], segment of row r starting d_dst_off[r]
+ * entries into those regions — and waits until every rank's segments have landed here. */
+int sb200_exchange_push_rows(sb200_exchange* x, void* cuda_stream, const int32_t* d_p_loc, const int32_t* d_cols,
+                             const double* d_vals, const int64_t* d_dst_off, int32_t nrow, int32_t col_offset,
+                             const int32_t* row_bounds /* world + 1, host */, const int64_t* cols_offsets /* world, host */,
+                             const int64_t* vals_offsets /* world, host */);
 int sb200_exchange_barrier(sb200_exchange* x, void* cuda_stream);
 /* Synchronises the device; SB200_E_CUDA if a barrier gave up waiting for a peer.  A barrier that sees no signal
  * from a peer for SB200_EXCHANGE_TIMEOUT_S seconds (default 600) raises the window's error word and traps its kernel: the

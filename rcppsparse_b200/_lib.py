@@ -28,7 +28,7 @@ SYMBOLS = [
     "sb200_sharded_create", "sb200_sharded_destroy", "sb200_sharded_info", "sb200_sharded_block", "sb200_sharded_col_sums",
     "sb200_sharded_row_sums", "sb200_sharded_col_means", "sb200_sharded_row_means", "sb200_sharded_spmv", "sb200_sharded_spmv_t",
     "sb200_exchange_create", "sb200_exchange_connect", "sb200_exchange_destroy", "sb200_exchange_window",
-    "sb200_exchange_gather", "sb200_exchange_reduce", "sb200_exchange_barrier", "sb200_exchange_status",
+    "sb200_exchange_gather", "sb200_exchange_reduce", "sb200_exchange_push_rows", "sb200_exchange_barrier", "sb200_exchange_status",
 ]
 
 
@@ -111,6 +111,7 @@ def lib() -> C.CDLL:
         "sb200_exchange_window": ([vp, pp, C.POINTER(i64), C.POINTER(i64)], C.c_int),
         "sb200_exchange_gather": ([vp, vp, i64, i64, i64], C.c_int),
         "sb200_exchange_reduce": ([vp, vp, i64, i64, i64, dbl], C.c_int),
+        "sb200_exchange_push_rows": ([vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp], C.c_int),
         "sb200_exchange_barrier": ([vp, vp], C.c_int),
         "sb200_exchange_status": ([vp], C.c_int),
     }

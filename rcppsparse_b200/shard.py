@@ -388,6 +388,10 @@ class ShardedMatrix:
         all-to-all-v of (column id, value) pairs, and an index gather that interleaves the received
         per-rank segments row by row.
 
+        With the peer-memory exchange (CUDA ranks of one node) the data never goes through a collective: every rank
+        pushes its segment of every row straight to the row's final place in the owner's window (``_transpose_push``,
+        ``sb200_exchange_push_rows``); only the per-rank row counts (8 bytes per row and rank) are all-gathered.
+
         Returns (row_bounds, p, cols, vals): this rank owns output columns (= rows of A)
         [row_bounds[rank], row_bounds[rank+1]); p is rebased to 0; cols are GLOBAL column ids of A."""
         W, rank, dev = self.world, self.rank, self.device
@@ -411,6 +415,8 @@ class ShardedMatrix:
         for k in range(1, len(rb)):
             rb[k] = max(rb[k], rb[k - 1])
         r0, r1 = rb[rank], rb[rank + 1]
+        if self.window is not None and W > 1:
+            return self._transpose_push(rb, P, all_counts, tp, tcols, tvals)
         # what I send to rank k: my entries of rows [rb[k], rb[k+1]) — one contiguous slice of my local transpose
         send_off = [int(tp64[rb[k]]) for k in range(W + 1)]
         send_splits = [send_off[k + 1] - send_off[k] for k in range(W)]
@@ -439,3 +445,45 @@ class ShardedMatrix:
             src_index = torch.repeat_interleave(seg_src - seg_dst, seg_len) + torch.arange(n_recv, device=dev)
             rcols, rvals = rcols[src_index], rvals[src_index]
         return rb, p_own.to(torch.int32), rcols, rvals
+
+    def _transpose_push(self, rb, P, all_counts, tp, tcols, tvals):
+        """The exchange step of the sharded transpose as P2P stores (sb200_exchange_push_rows): output row r is the
+        concatenation, in rank (= column) order, of the ranks' segments of row r; my segment of row r starts
+        (P[r] - P[first row of the owner's block]) + sum of the counts of the ranks before me, inside the owner's output."""
+        W, rank, dev = self.world, self.rank, self.device
+        lib = self.window._lib
+        n_out = [int(P[rb[q + 1]] - P[rb[q]]) for q in range(W)]
+        align = lambda b: (b + 255) & ~255  # noqa: E731
+        # one window per rank for its block of the result: [int32 column ids | float64 values] behind the header
+        win = PeerWindow(dev, rank, W, align(4 * n_out[rank]) + 8 * n_out[rank] + 512, self.group)
+        try:
+            data0 = win._cursor
+            cols_off = [data0] * W
+            vals_off = [data0 + align(4 * n_out[q]) for q in range(W)]
+            before_me = all_counts[:rank].sum(dim=0) if rank > 0 else torch.zeros(self.nrow, dtype=torch.int64, device=dev)
+            block_start = torch.empty(self.nrow, dtype=torch.int64, device=dev)
+            for q in range(W):
+                block_start[rb[q]:rb[q + 1]] = P[rb[q]]
+            dst_off = (P[:-1] - block_start + before_me).contiguous()
+            rb_h = np.asarray(rb, np.int32)
+            co_h, vo_h = np.asarray(cols_off, np.int64), np.asarray(vals_off, np.int64)
+            tp32 = tp.to(torch.int32).contiguous()
+            st = torch.cuda.current_stream(dev)
+            lib.check(lib.lib().sb200_exchange_push_rows(
+                win._h, C.c_void_p(st.cuda_stream), C.c_void_p(tp32.data_ptr()), C.c_void_p(tcols.data_ptr() if tcols.numel() else 0),
+                C.c_void_p(tvals.data_ptr() if tvals.numel() else 0), C.c_void_p(dst_off.data_ptr()), self.nrow, self.c0,
+                C.c_void_p(rb_h.ctypes.data), C.c_void_p(co_h.ctypes.data), C.c_void_p(vo_h.ctypes.data)))
+            n = n_out[rank]
+            if n > 0:  # the kernel's closing barrier (in stream order) says every rank's segments have landed here
+                rcols = torch.as_tensor(_CudaView(win.base + cols_off[rank], n, "<i4"), device=dev).clone()
+                rvals = torch.as_tensor(_CudaView(win.base + vals_off[rank], n, "<f8"), device=dev).clone()
+            else:
+                rcols = torch.empty(0, dtype=torch.int32, device=dev)
+                rvals = torch.empty(0, dtype=torch.float64, device=dev)
+            win.status()
+        finally:
+            dist.barrier(group=self.group)  # nobody unmaps while a peer may still write
+            win.close()
+        r0, r1 = rb[rank], rb[rank + 1]
+        p_own = (P[r0:r1 + 1] - P[r0]).to(torch.int32)
+        return rb, p_own, rcols, rvals

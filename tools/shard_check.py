@@ -56,7 +56,8 @@ def main():
                     ref = mine.clone()
                     dist.broadcast(ref, src=0)
                     assert torch.equal(mine.view(torch.int64), ref.view(torch.int64)), f"{op}: ranks disagree bitwise"
-            # sharded transpose (local device transposes + one NCCL all-to-all-v): my rows, bit for bit
+            # sharded transpose: local device transposes + one exchange step (P2P segment pushes on the peer-memory
+            # exchange, an NCCL all-to-all-v on the collective one): my rows, bit for bit
             rb, tp_own, tcols, tvals = S.transpose()
             fi, fp, fx = chk.transpose(*args)
             r0, r1 = rb[rank], rb[rank + 1]
