@@ -1285,6 +1285,10 @@ void free_matrix_plans(sb200_matrix* m, cudaStream_t s) {
     free_band_plan(m->plan_transpose, s);
     m->plan_transpose = nullptr;
   }
+  if (m->plan_split) {
+    free_split_plan(m->plan_split, s);
+    m->plan_split = nullptr;
+  }
 }
 
 }  // namespace sb200

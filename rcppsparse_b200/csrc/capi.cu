@@ -708,7 +708,7 @@ int sb200_matrix_layouts(sb200_matrix* m, int* mask) {
   ENTER(m);
   if (!mask) return fail(SB200_E_INVALID, "mask is NULL");
   *mask = (m->rows_state == 1 ? 1 : 0) | (m->bmc_state == 1 ? 2 : 0) |
-          ((m->rows_state == 1 && m->rows && m->rows->bmc_state == 1) ? 4 : 0) | (m->plan_transpose ? 8 : 0);
+          ((m->rows_state == 1 && m->rows && m->rows->bmc_state == 1) ? 4 : 0) | ((m->plan_transpose || m->plan_split) ? 8 : 0);
   return SB200_OK;
 }
 

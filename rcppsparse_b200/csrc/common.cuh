@@ -53,6 +53,7 @@ constexpr int NUM_SMS_B200 = 148;
 // ---------------------------------------------------------------------------------------------
 struct BandPlan;       // bands.cu
 struct BandCompanion;  // bmc.cu
+struct SplitPlan;      // transpose_split.cu
 
 }  // namespace sb200
 
@@ -100,6 +101,7 @@ struct sb200_matrix {
   int bmc_state;      // 0 not built, 1 built, -1 never
   int spmv_t_calls;   // A^T v calls served by the L2-gather sweep since the last (re)build decision
   sb200::BandPlan* plan_transpose;  // band plan of the transpose, kept between calls (structure only)
+  sb200::SplitPlan* plan_split;     // same for the two-split transpose of tall matrices (transpose_split.cu)
 };
 
 namespace sb200 {
@@ -153,6 +155,11 @@ void drop_band_companion(sb200_matrix* m, cudaStream_t s);
 int launch_bandsweep(sb200_matrix* m, const double* d_v, double* d_out);  // y[ncol] = A^T v from the companion
 int64_t band_companion_bytes(const sb200_matrix* m);                    // HBM the companion occupies (0 without one)
 void free_matrix_plans(sb200_matrix* m, cudaStream_t s);
+// transpose_split.cu: two stable stream splits (tall matrices)
+bool split_transpose_fits(const sb200_matrix* m);
+int transpose_split_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double* d_x_out);
+void free_split_plan(SplitPlan* sp, cudaStream_t s);
+int64_t split_plan_bytes(const SplitPlan* sp);
 // hostcopy.cu: pageable host memory through worker threads with pinned chunks (blocking)
 bool host_is_pageable(const void* p);
 int staged_h2d(int device, void* d_dst, const void* h_src, size_t bytes);

@@ -582,16 +582,20 @@ struct PhaseTimer {  // SB200_TRACE=1: device time of the plan and of the placem
 
 }  // namespace
 
-// kind: 1 = banded two-pass kernel of bands.cu (2432-row bands), 2 = chunk-sort placement (384-row bands)
+// kind: 1 = banded two-pass kernel of bands.cu (2432-row bands), 2 = chunk-sort placement (384-row bands),
+// 3 = two stable stream splits (transpose_split.cu).  Tall matrices — too few entries per (column, 384-row band) for the
+// chunk sort — take 3 when its tables fit, else 1.
 static int transpose_kind(const sb200_matrix* m) {
   if (const char* e = getenv("SB200_TRANSPOSE_PATH")) {
     if (!strcmp(e, "banded") || !strcmp(e, "1")) return 1;
     if (!strcmp(e, "place") || !strcmp(e, "2")) return 2;
+    if ((!strcmp(e, "split") || !strcmp(e, "3")) && split_transpose_fits(m)) return 3;
   }
   // bands needed so that none exceeds 384 rows vs. bands that still leave ~2 entries per (column, band) run
   const double floor_bands = static_cast<double>(m->nrow) / (0.9 * PL_ROWS_CAP);
   const double by_density = static_cast<double>(m->nnz) / (2.0 * static_cast<double>(m->ncol > 0 ? m->ncol : 1));
-  return floor_bands <= by_density ? 2 : 1;
+  if (floor_bands <= by_density) return 2;
+  return split_transpose_fits(m) ? 3 : 1;
 }
 
 int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double* d_x_out) {
@@ -609,6 +613,7 @@ int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double
   PhaseTimer tr(st);
   tr.mark();
   const int kind = transpose_kind(m);
+  if (kind == 3) return transpose_split_device(m, d_p_out, d_i_out, d_x_out);
   int env_bands = 0, env_splits = 0;
   if (const char* e = getenv("SB200_TRANSPOSE_SPLITS")) env_splits = atoi(e);
   if (const char* e = getenv("SB200_TRANSPOSE_BANDS")) env_bands = atoi(e);

@@ -1,0 +1,705 @@
+// CSC -> CSR transpose of TALL matrices: two stable stream splits (tools/transpose_two_level_spec.py is the
+// executable specification of the intermediate arrays).
+//
+// Replaces Matrix::transpose() of the reference (zdebruine/RcppSparse, RcppSparse.h:375-385; arithmetic = R's
+// Matrix::t, a serial counting sort by row) where the chunk-sorting kernel of transpose.cu has nothing to chew on: a
+// 1M-row matrix of density 1e-3 leaves 0.4 entries per (column, 384-row band), so a single pass can coalesce either
+// its reads or its writes, never both.  Two passes, both with contiguous reads and short contiguous runs on the way out:
+//
+//   pass 1  the entry stream in storage (column-major) order is cut into tiles of 4096 entries; every tile is split,
+//           stably, by ROW BAND (band = row >> sh, ~sqrt(nrow) rows each) and appends its piece of each band to that
+//           band's stream.  Where the piece goes is structure only: first slot of (tile, band) = exclusive scan over
+//           (band major, tile minor) of the per-tile band counts — kept on the handle.  Record: row inside the band
+//           (16 bits), source column (32), value (64).
+//   pass 2  a band's stream is cut into segments of 4 chunks; a CTA takes a segment, walks it 4096 records at a time and
+//           splits each chunk, stably, by row; a row's piece is appended at the row's cursor (shared memory).  Where the
+//           cursors of a segment start is structure only too: p'[row] + the row's records in the band's earlier segments
+//           (counted once, on the first call, from the record stream pass 1 has just written; kept on the handle).
+//
+// Both passes are the same kernel (split_kernel<PASS>).  The stable split of a chunk: warp w owns the w-th contiguous
+// 256 records; one ballot per key bit tells a lane which lanes of its 32-record step hold the same key (rank in lane =
+// storage order); a table of counts per
+// (warp, key) in shared memory — u16, touched by the key's lowest lane only — carries the rank across the steps of
+// a warp; one scan per key over the 16 warps and one block scan over the keys lay the chunk out key-major in a
+// shared-memory IMAGE; the image leaves linearly, so the records of one key are consecutive global stores.  Order
+// inside a key = storage order in both passes => inside an output row = source column order: the canonical CSC of
+// A^T bit for bit, no sort, no global atomics.  No floating-point arithmetic.
+//
+// Roofline: HBM.  Algorithmic bytes 24N + 4(n+1) + 4(m+1); this path moves 12N + 14N + 14N + 12N plus
+// 4 bytes per (tile, band), so its ceiling is 0.46 of that roofline.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sb200 {
+
+struct SplitPlan {
+  int sh = 0;           // rows per band = 1 << sh
+  int nb = 0;           // bands
+  int te = 0;           // entries per tile
+  int64_t ntiles = 0;
+  int32_t* d_rowptr = nullptr;   // [nrow+1] p' of the result
+  int32_t* d_tb = nullptr;       // [ntiles*nb] tile-major: first slot, in the band-major record stream, of (tile, band)
+  int32_t* d_bstart = nullptr;   // [nb+1] where every band's stream starts
+  int32_t* d_tilecol = nullptr;  // [ntiles+1] column holding the first entry of tile t
+  int seg_chunks = 0;
+  int nseg = 0;                  // pass-2 units: pieces of <= SP_SEG_CHUNKS chunks of one band's stream
+  int32_t* d_seg = nullptr;      // [3*nseg] band, first record, end of every segment
+  int32_t* d_segfirst = nullptr; // [nb+1] first segment of every band
+  uint32_t* d_segcur = nullptr;  // [nseg << sh] where every row's cursor starts in a segment (filled on the first call)
+  bool segcur_ready = false;
+  unsigned int* d_counters = nullptr;  // [2] tickets of the two passes
+  size_t bytes = 0;
+};
+
+namespace {
+
+constexpr int SP_THREADS = 512;
+constexpr int SP_TE = 4096;
+constexpr int SP_SEG_CHUNKS = 4;  // chunks per pass-2 unit (SB200_SPLIT_SEG)
+constexpr int SP_MAX_KEYS = 3072;  // bands, and rows per band: the (warp, key) table is 16 x keys x 2 bytes of shared memory
+
+__device__ __forceinline__ uint32_t ld_stream_u16(const uint16_t* p) {
+  uint16_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+
+// ---- plan kernels -----------------------------------------------------------------------------------------------
+// Hc[b * ntiles + t] = entries of tile t in band b;  rowcnt[r] += 1 per entry
+__global__ void __launch_bounds__(SP_THREADS)
+    split_hist_kernel(const int32_t* __restrict__ gi, int64_t nnz, int sh, int nb, int te, int64_t ntiles,
+                      uint32_t* __restrict__ hc, uint32_t* __restrict__ rowcnt) {
+  extern __shared__ uint32_t hist[];
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (int b = threadIdx.x; b < nb; b += SP_THREADS) hist[b] = 0u;
+    __syncthreads();
+    const int64_t k0 = t * te;
+    const int n = static_cast<int>((nnz - k0 < te) ? nnz - k0 : te);
+    for (int q = threadIdx.x; q < n; q += SP_THREADS) {
+      const int32_t r = ptx::ld_stream_s32(gi + k0 + q);
+      atomicAdd(&hist[r >> sh], 1u);
+      ptx::red_add_u32(rowcnt + r, 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += SP_THREADS) hc[static_cast<int64_t>(b) * ntiles + t] = hist[b];
+    __syncthreads();
+  }
+}
+
+// tb[t * nb + b] = scan[b * ntiles + t] (32 x 32 tiles through shared memory); bstart[b] = scan[b * ntiles]
+__global__ void __launch_bounds__(256)
+    split_table_kernel(const int32_t* __restrict__ scan, int nb, int64_t ntiles, int32_t nnz, int32_t* __restrict__ tb,
+                       int32_t* __restrict__ bstart) {
+  __shared__ int32_t tile[32][33];
+  const int64_t t0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int b0 = blockIdx.y * 32;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ly; j < 32; j += 8) {
+    const int b = b0 + j;
+    const int64_t t = t0 + lx;
+    if (b < nb && t < ntiles) tile[j][lx] = scan[static_cast<int64_t>(b) * ntiles + t];
+  }
+  __syncthreads();
+  for (int j = ly; j < 32; j += 8) {
+    const int64_t t = t0 + j;
+    const int b = b0 + lx;
+    if (b < nb && t < ntiles) tb[t * nb + b] = tile[lx][j];
+  }
+  if (blockIdx.x == 0 && ly == 0) {
+    const int b = b0 + lx;
+    if (b < nb) bstart[b] = scan[static_cast<int64_t>(b) * ntiles];
+    if (b == nb - 1) bstart[nb] = nnz;
+  }
+}
+
+// tilecol[t] = the column holding entry t * te (largest c < ncol with p[c] <= t * te)
+__global__ void split_tilecol_kernel(const int32_t* __restrict__ gp, int32_t ncol, int64_t nnz, int te, int64_t ntiles,
+                                     int32_t* __restrict__ tilecol) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t > ntiles) return;
+  int64_t k = t * te;
+  if (k > nnz) k = nnz;
+  int32_t lo = 0, hi = ncol - 1;
+  while (lo < hi) {
+    const int32_t mid = lo + ((hi - lo + 1) >> 1);
+    if (gp[mid] <= k)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  tilecol[t] = lo;
+}
+
+// h[(seg << sh) + r] = records of row r (inside its band) in segment seg of the record stream
+__global__ void __launch_bounds__(SP_THREADS)
+    split_seg_hist_kernel(const uint16_t* __restrict__ s_r, const int32_t* __restrict__ seg, int nseg, int sh, uint32_t* __restrict__ h) {
+  extern __shared__ uint32_t hist[];
+  const int R = 1 << sh;
+  for (int u = blockIdx.x; u < nseg; u += gridDim.x) {
+    for (int r = threadIdx.x; r < R; r += SP_THREADS) hist[r] = 0u;
+    __syncthreads();
+    const int64_t k0 = seg[3 * u + 1], k1 = seg[3 * u + 2];
+    for (int64_t k = k0 + threadIdx.x; k < k1; k += SP_THREADS) atomicAdd(&hist[ld_stream_u16(s_r + k)], 1u);
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += SP_THREADS) h[(static_cast<int64_t>(u) << sh) + r] = hist[r];
+    __syncthreads();
+  }
+}
+
+// counts -> cursors: per (band, row), p'[row] then the running sum over the band's segments
+__global__ void split_seg_scan_kernel(uint32_t* __restrict__ h, const int32_t* __restrict__ segfirst, const int32_t* __restrict__ rowptr,
+                                      int32_t nrow, int sh) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= nrow) return;
+  const int b = static_cast<int>(row >> sh), r = static_cast<int>(row & ((1 << sh) - 1));
+  uint32_t run = static_cast<uint32_t>(rowptr[row]);
+  for (int u = segfirst[b]; u < segfirst[b + 1]; ++u) {
+    uint32_t* cell = h + (static_cast<int64_t>(u) << sh) + r;
+    const uint32_t c = *cell;
+    *cell = run;
+    run += c;
+  }
+}
+
+// ---- the stable split ---------------------------------------------------------------------------------------------
+struct SplitArgs {
+  const int32_t* i;  // pass 1 input: the mirror
+  const int32_t* p;
+  const double* x;
+  uint16_t* s_r;     // band-major record stream (pass 1 writes, pass 2 reads)
+  int32_t* s_c;
+  double* s_x;
+  int32_t* i_out;    // pass 2 output
+  double* x_out;
+  const int32_t* tb;
+  const int32_t* bstart;
+  const int32_t* tilecol;
+  const int32_t* seg;
+  const uint32_t* segcur;
+  int nseg;
+  const int32_t* rowptr;
+  int64_t ntiles;
+  int64_t nnz;
+  int32_t nrow, ncol;
+  int sh, nb;
+  int keys;  // keys of this pass (bands / rows per band)
+  int kp;    // table pitch: keys rounded up to a multiple of 8
+  int kbits; // bits that tell the keys apart
+  unsigned int* counter;
+};
+
+template <int PASS>
+size_t split_smem_bytes(int kp) {
+  return static_cast<size_t>(SP_TE) * (8 + 4 + 2 + (PASS == 1 ? 2 : 0)) + static_cast<size_t>(kp) * 4 * 3 +
+         static_cast<size_t>(SP_THREADS / 32) * kp * 2;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(SP_THREADS, 2) split_kernel(const SplitArgs a) {
+  constexpr int THREADS = SP_THREADS, TE = SP_TE;
+  constexpr int W = THREADS / 32, EPT = TE / THREADS, SEG = EPT * 32;
+  extern __shared__ __align__(16) unsigned char ssm[];
+  __shared__ uint32_t wscan[W];
+  __shared__ unsigned int s_unit;
+
+  const int K = a.keys, KP = a.kp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  double* img_x = reinterpret_cast<double*>(ssm);                    // [TE] the chunk's output image: values,
+  int32_t* img_c = reinterpret_cast<int32_t*>(img_x + TE);           // [TE] source columns,
+  uint32_t* img_kr = reinterpret_cast<uint32_t*>(img_c + TE);        // [TE] pass 1: key << 16 | row inside the band
+  uint16_t* img_k = reinterpret_cast<uint16_t*>(img_c + TE);         // [TE] pass 2: keys (to find a slot's global address)
+  uint32_t* kbase = reinterpret_cast<uint32_t*>(img_k + (PASS == 1 ? 2 * TE : TE));  // [KP] where a key's piece starts in the image
+  int32_t* gdelta = reinterpret_cast<int32_t*>(kbase + KP);          // [KP] global slot - image slot
+  uint32_t* cur = reinterpret_cast<uint32_t*>(gdelta + KP);          // [KP] next free global slot of every key
+  uint16_t* tbl = reinterpret_cast<uint16_t*>(cur + KP);             // [W*KP] records of (warp, key), then its offset
+  const int tbl_vec = (W * KP * 2) / 16;
+
+  for (int e = tid; e < tbl_vec; e += THREADS) reinterpret_cast<uint4*>(tbl)[e] = make_uint4(0u, 0u, 0u, 0u);
+
+  // one chunk: records [k0, k0 + n) of the input stream; cur[] holds every key's destination
+  auto chunk = [&](const int64_t k0, const int n, const int32_t tc0, const int32_t tc1, const int64_t next0, const int next_n) {
+    // ---- load: warp w owns records [w * SEG, (w + 1) * SEG), 32 consecutive ones per step -----------------------
+    uint32_t kr[EPT];  // key << 16 | row inside the band (pass 1)
+    uint32_t rk[EPT];  // rank inside (warp, key)
+    int32_t cc[EPT];
+    double xx[EPT];
+    const int seg0 = warp * SEG + lane;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      const int q = seg0 + j * 32;
+      kr[j] = 0xffffffffu;
+      cc[j] = 0;
+      xx[j] = 0.0;
+      if (q < n) {
+        if (PASS == 1) {
+          const int32_t r = ptx::ld_stream_s32(a.i + k0 + q);
+          kr[j] = (static_cast<uint32_t>(r >> a.sh) << 16) | static_cast<uint32_t>(r & ((1 << a.sh) - 1));
+          xx[j] = ptx::ld_stream_f64(a.x + k0 + q);
+        } else {
+          kr[j] = ld_stream_u16(a.s_r + k0 + q) << 16;
+          cc[j] = ptx::ld_stream_s32(a.s_c + k0 + q);
+          xx[j] = ptx::ld_stream_f64(a.s_x + k0 + q);
+        }
+      }
+    }
+    // the records this CTA takes next, on their way to L2 (one 128-byte line per thread and array)
+    if (next_n > 0) {
+      const int64_t e0 = next0 & ~int64_t(15);  // first record of the 128-byte line of doubles holding next0
+      const int64_t e = e0 + static_cast<int64_t>(tid) * 16;
+      if (e < next0 + next_n) {
+        if (PASS == 1) {
+          ptx::prefetch_l2(a.x + e);
+          if (!(tid & 1)) ptx::prefetch_l2(a.i + e);
+        } else {
+          ptx::prefetch_l2(a.s_x + e);
+          if (!(tid & 1)) ptx::prefetch_l2(a.s_c + e);
+          if (!(tid & 3)) ptx::prefetch_l2(a.s_r + e);
+        }
+      }
+    }
+    if (PASS == 1 && seg0 < n) {
+      // column of my first record by bisection inside the tile's columns, then walk: columns are long here
+      const int64_t kf = k0 + seg0;
+      int32_t lo = tc0, hi = tc1;
+      while (lo < hi) {
+        const int32_t mid = lo + ((hi - lo + 1) >> 1);
+        if (__ldg(a.p + mid) <= kf)
+          lo = mid;
+        else
+          hi = mid - 1;
+      }
+      int32_t c = lo;
+      int64_t pend = __ldg(a.p + c + 1);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int q = seg0 + j * 32;
+        if (q < n) {
+          const int64_t k = k0 + q;
+          while (k >= pend) {
+            ++c;
+            pend = __ldg(a.p + c + 1);
+          }
+          cc[j] = c;
+        }
+      }
+    }
+    // ---- rank inside the warp: equal keys of a step in lane order, steps in order ----------------------------------
+    // Which lanes hold my key: one ballot per key bit.  (match.any does this in one instruction, but with ~32 distinct
+    // keys per step — the normal case here — it held the XU pipe ~200 cycles per call and WAS the kernel's run time:
+    // profiles/r02/prof_split_v1_c2.summary.txt.)
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      const bool valid = kr[j] != 0xffffffffu;
+      const uint32_t key = kr[j] >> 16;
+      unsigned same = __ballot_sync(0xffffffffu, valid);
+      for (int b = 0; b < a.kbits; ++b) {
+        const bool bit = (key >> b) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, bit);
+        same &= bit ? bal : ~bal;
+      }
+      uint16_t* slot = tbl + warp * KP + (valid ? key : 0u);
+      const uint32_t old = *slot;  // every lane of the group reads, its lowest lane writes
+      __syncwarp();
+      if (valid && (same & lt_mask) == 0u) *slot = static_cast<uint16_t>(old + __popc(same));
+      rk[j] = old + __popc(same & lt_mask);
+      __syncwarp();
+    }
+    __syncthreads();
+    // ---- per key: the warps' pieces in warp order; block scan over the keys -> image layout, destinations ----------
+    // A thread owns 8 consecutive keys: their u16 counts are four 32-bit words, and no sum reaches 65536, so the
+    // scan over the warps is four plain adds per warp.
+    uint32_t mytot = 0;
+    uint4 tot4 = make_uint4(0u, 0u, 0u, 0u);
+    const bool owner = tid * 8 < KP;
+    if (owner) {
+      uint4* col = reinterpret_cast<uint4*>(tbl + tid * 8);
+      const int pitch = KP / 8;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const uint4 c = col[w * pitch];
+        col[w * pitch] = tot4;
+        tot4.x += c.x;
+        tot4.y += c.y;
+        tot4.z += c.z;
+        tot4.w += c.w;
+      }
+      mytot = (tot4.x & 0xffffu) + (tot4.x >> 16) + (tot4.y & 0xffffu) + (tot4.y >> 16) + (tot4.z & 0xffffu) + (tot4.z >> 16) +
+              (tot4.w & 0xffffu) + (tot4.w >> 16);
+    }
+    uint32_t incl = mytot;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += up;
+    }
+    if (lane == 31) wscan[warp] = incl;
+    __syncthreads();
+    if (owner) {
+      uint32_t base = incl - mytot;
+#pragma unroll
+      for (int w = 0; w < W; ++w)
+        if (w < warp) base += wscan[w];
+      const uint32_t t8[8] = {tot4.x & 0xffffu, tot4.x >> 16, tot4.y & 0xffffu, tot4.y >> 16,
+                              tot4.z & 0xffffu, tot4.z >> 16, tot4.w & 0xffffu, tot4.w >> 16};
+      uint32_t kb[8], c0[8];
+      *reinterpret_cast<uint4*>(c0) = *reinterpret_cast<const uint4*>(cur + tid * 8);
+      *reinterpret_cast<uint4*>(c0 + 4) = *reinterpret_cast<const uint4*>(cur + tid * 8 + 4);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        kb[e] = base;
+        base += t8[e];
+      }
+      *reinterpret_cast<uint4*>(kbase + tid * 8) = make_uint4(kb[0], kb[1], kb[2], kb[3]);
+      *reinterpret_cast<uint4*>(kbase + tid * 8 + 4) = make_uint4(kb[4], kb[5], kb[6], kb[7]);
+      *reinterpret_cast<uint4*>(gdelta + tid * 8) = make_uint4(c0[0] - kb[0], c0[1] - kb[1], c0[2] - kb[2], c0[3] - kb[3]);
+      *reinterpret_cast<uint4*>(gdelta + tid * 8 + 4) = make_uint4(c0[4] - kb[4], c0[5] - kb[5], c0[6] - kb[6], c0[7] - kb[7]);
+      if (PASS == 2) {
+        *reinterpret_cast<uint4*>(cur + tid * 8) = make_uint4(c0[0] + t8[0], c0[1] + t8[1], c0[2] + t8[2], c0[3] + t8[3]);
+        *reinterpret_cast<uint4*>(cur + tid * 8 + 4) = make_uint4(c0[4] + t8[4], c0[5] + t8[5], c0[6] + t8[6], c0[7] + t8[7]);
+      }
+    }
+    __syncthreads();
+    // ---- place into the image ---------------------------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      if (kr[j] != 0xffffffffu) {
+        const uint32_t key = kr[j] >> 16;
+        const uint32_t pos = kbase[key] + tbl[warp * KP + key] + rk[j];
+        img_x[pos] = xx[j];
+        img_c[pos] = cc[j];
+        if (PASS == 1)
+          img_kr[pos] = kr[j];
+        else
+          img_k[pos] = static_cast<uint16_t>(key);
+      }
+    }
+    __syncthreads();
+    // ---- flush: consecutive image slots of a key are consecutive global slots; clear the table ----------------------------
+    for (int pp = tid; pp < n; pp += THREADS) {
+      const uint32_t kw = PASS == 1 ? img_kr[pp] : static_cast<uint32_t>(img_k[pp]) << 16;
+      const int64_t g = static_cast<int64_t>(static_cast<uint32_t>(gdelta[kw >> 16] + pp));
+      if (PASS == 1) {
+        a.s_r[g] = static_cast<uint16_t>(kw & 0xffffu);
+        a.s_c[g] = img_c[pp];
+        a.s_x[g] = img_x[pp];
+      } else {
+        a.i_out[g] = img_c[pp];
+        a.x_out[g] = img_x[pp];
+      }
+    }
+    for (int e = tid; e < tbl_vec; e += THREADS) reinterpret_cast<uint4*>(tbl)[e] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+  };
+
+  for (;;) {
+    if (tid == 0) s_unit = atomicAdd(a.counter, 1u);
+    __syncthreads();  // also: the table is clear, the previous chunk's image has left
+    const int64_t u = s_unit;
+    if (PASS == 1) {
+      if (u >= a.ntiles) break;
+      const int64_t k0 = u * TE;
+      const int n = static_cast<int>((a.nnz - k0 < TE) ? a.nnz - k0 : TE);
+      for (int b = tid; b < K; b += THREADS) cur[b] = static_cast<uint32_t>(__ldg(a.tb + u * a.nb + b));
+      const int64_t un = u + gridDim.x;  // tickets go out in order: about where this CTA's next tile will be
+      const int64_t kn = un * TE;
+      chunk(k0, n, __ldg(a.tilecol + u), __ldg(a.tilecol + u + 1), kn, un < a.ntiles ? static_cast<int>((a.nnz - kn < TE) ? a.nnz - kn : TE) : 0);
+    } else {
+      if (u >= a.nseg) break;
+      const int R = 1 << a.sh;
+      const int64_t s0 = __ldg(a.seg + 3 * u + 1), s1 = __ldg(a.seg + 3 * u + 2);
+      for (int r = tid; r < R; r += THREADS) cur[r] = __ldg(a.segcur + (u << a.sh) + r);
+      for (int64_t k0 = s0; k0 < s1; k0 += TE) {
+        const int64_t kn = k0 + TE;
+        chunk(k0, static_cast<int>((s1 - k0 < TE) ? s1 - k0 : TE), 0, 0, kn, kn < s1 ? static_cast<int>((s1 - kn < TE) ? s1 - kn : TE) : 0);
+      }
+    }
+  }
+}
+
+struct Trace {  // SB200_TRACE=1: device time of the plan and of the two passes on stderr
+  bool on;
+  cudaStream_t st;
+  cudaEvent_t ev[4];
+  int n = 0;
+  explicit Trace(cudaStream_t s) : on(getenv("SB200_TRACE") != nullptr), st(s) {}
+  void mark() {
+    if (!on || n >= 4) return;
+    cudaEventCreate(&ev[n]);
+    cudaEventRecord(ev[n++], st);
+  }
+  void report(const SplitPlan* sp, bool cached) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[sb200 trace] transpose (%s, two stream splits) rows/band=%d bands=%d tiles=%lld plan=%.1f MB:", cached ? "cached plan" : "plan built",
+            1 << sp->sh, sp->nb, static_cast<long long>(sp->ntiles), sp->bytes / 1048576.0);
+    static const char* names[] = {"plan", "pass1", "pass2"};
+    for (int k = 1; k < n; ++k) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[k - 1], ev[k]);
+      fprintf(stderr, " %s %.3f ms;", names[k - 1], ms);
+    }
+    fprintf(stderr, "\n");
+    for (int k = 0; k < n; ++k) cudaEventDestroy(ev[k]);
+  }
+};
+
+int key_bits(int keys) {
+  int b = 0;
+  while ((1 << b) < keys) ++b;
+  return b;
+}
+
+int segment_chunks() {
+  if (const char* e = getenv("SB200_SPLIT_SEG")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 4096) return v;
+  }
+  return SP_SEG_CHUNKS;
+}
+
+int band_shift(const sb200_matrix* m) {
+  int sh = 0;
+  while ((static_cast<int64_t>(1) << (2 * sh)) < m->nrow) ++sh;  // 2^sh >= sqrt(nrow): bands ~ rows per band
+  if (const char* e = getenv("SB200_SPLIT_SHIFT")) {
+    const int v = atoi(e);
+    if (v >= 0 && v <= 16) sh = v;
+  }
+  return sh;
+}
+
+}  // namespace
+
+void free_split_plan(SplitPlan* sp, cudaStream_t s) {
+  if (!sp) return;
+  pool_free(sp->d_rowptr, s);
+  pool_free(sp->d_tb, s);
+  pool_free(sp->d_bstart, s);
+  pool_free(sp->d_tilecol, s);
+  pool_free(sp->d_seg, s);
+  pool_free(sp->d_segfirst, s);
+  pool_free(sp->d_segcur, s);
+  pool_free(sp->d_counters, s);
+  delete sp;
+}
+
+int64_t split_plan_bytes(const SplitPlan* sp) { return sp ? static_cast<int64_t>(sp->bytes) : 0; }
+
+// Whether the two-split path can take this matrix: key tables within shared memory, the (tile, band) table and the
+// record stream within what the device has left.
+bool split_transpose_fits(const sb200_matrix* m) {
+  if (m->nnz <= 0 || m->nrow <= 0) return false;
+  const int sh = band_shift(m);
+  const int64_t rb = static_cast<int64_t>(1) << sh;
+  const int64_t nb = (m->nrow + rb - 1) >> sh;
+  if (rb > SP_MAX_KEYS || nb > SP_MAX_KEYS) return false;
+  const int64_t ntiles = (m->nnz + SP_TE - 1) / SP_TE;
+  const size_t table = sizeof(int32_t) * static_cast<size_t>(nb) * static_cast<size_t>(ntiles);
+  const size_t stream = 14ull * static_cast<size_t>(m->nnz);
+  const size_t need = (m->plan_split ? 0 : 3 * table) + stream + (64ull << 20);
+  return device_free_bytes() > need + need / 8;
+}
+
+static int build_split_plan(sb200_matrix* m, SplitPlan** out) {
+  cudaStream_t st = m->stream;
+  SplitPlan* sp = new (std::nothrow) SplitPlan();
+  if (!sp) return fail(SB200_E_NOMEM, "transpose: out of host memory");
+  sp->sh = band_shift(m);
+  sp->nb = static_cast<int>((static_cast<int64_t>(m->nrow) + (1 << sp->sh) - 1) >> sp->sh);
+  sp->te = SP_TE;
+  sp->ntiles = (m->nnz + SP_TE - 1) / SP_TE;
+  const int nb = sp->nb;
+  const int64_t nt = sp->ntiles, cells = static_cast<int64_t>(nb) * nt;
+  uint32_t *d_hc = nullptr, *d_rowcnt = nullptr;
+  int32_t* d_scan = nullptr;
+  void* d_ws = nullptr;
+  auto drop = [&]() {
+    pool_free(d_hc, st);
+    pool_free(d_rowcnt, st);
+    pool_free(d_scan, st);
+    pool_free(d_ws, st);
+  };
+  struct Guard {
+    SplitPlan** sp;
+    cudaStream_t st;
+    decltype(drop)& fn;
+    bool armed = true;
+    ~Guard() {
+      fn();
+      if (armed) {
+        free_split_plan(*sp, st);
+        *sp = nullptr;
+      }
+    }
+  } guard{&sp, st, drop};
+  const size_t ws_bytes = scan_workspace_bytes(cells > m->nrow ? cells : m->nrow);
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&d_hc), sizeof(uint32_t) * static_cast<size_t>(cells), st));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&d_rowcnt), sizeof(uint32_t) * static_cast<size_t>(m->nrow), st));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&d_scan), sizeof(int32_t) * (static_cast<size_t>(cells) + 1), st));
+  SB_TRY(pool_alloc(&d_ws, ws_bytes, st));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&sp->d_rowptr), sizeof(int32_t) * (static_cast<size_t>(m->nrow) + 1), st));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&sp->d_tb), sizeof(int32_t) * static_cast<size_t>(cells), st));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&sp->d_bstart), sizeof(int32_t) * (nb + 1), st));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&sp->d_tilecol), sizeof(int32_t) * (static_cast<size_t>(nt) + 1), st));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&sp->d_counters), sizeof(unsigned int) * 2, st));
+  sp->bytes = sizeof(int32_t) * (static_cast<size_t>(m->nrow) + 1 + static_cast<size_t>(cells) + nb + 1 + static_cast<size_t>(nt) + 1) + 8;
+
+  SB_CUDA(cudaMemsetAsync(d_rowcnt, 0, sizeof(uint32_t) * static_cast<size_t>(m->nrow), st));
+  int64_t grid = nt < static_cast<int64_t>(m->sm_count) * 4 ? nt : static_cast<int64_t>(m->sm_count) * 4;
+  split_hist_kernel<<<static_cast<unsigned>(grid), SP_THREADS, sizeof(uint32_t) * nb, st>>>(m->d_i, m->nnz, sp->sh, nb, SP_TE, nt, d_hc, d_rowcnt);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  SB_TRY(exclusive_scan_u32(st, d_rowcnt, sp->d_rowptr, m->nrow, nullptr, d_ws, ws_bytes));
+  SB_TRY(exclusive_scan_u32(st, d_hc, d_scan, cells, nullptr, d_ws, ws_bytes));
+  {
+    const dim3 g(static_cast<unsigned>((nt + 31) / 32), static_cast<unsigned>((nb + 31) / 32));
+    split_table_kernel<<<g, 256, 0, st>>>(d_scan, nb, nt, static_cast<int32_t>(m->nnz), sp->d_tb, sp->d_bstart);
+    count_launch();
+    SB_CUDA(cudaGetLastError());
+  }
+  split_tilecol_kernel<<<static_cast<unsigned>((nt + 1 + 255) / 256), 256, 0, st>>>(m->d_p, m->ncol, m->nnz, SP_TE, nt, sp->d_tilecol);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  // pass-2 units: every band's stream in segments of SP_SEG_CHUNKS chunks
+  std::vector<int32_t> bs(static_cast<size_t>(nb) + 1), seg, segfirst(static_cast<size_t>(nb) + 1);
+  SB_CUDA(cudaMemcpyAsync(bs.data(), sp->d_bstart, sizeof(int32_t) * (nb + 1), cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  const int seg_chunks = segment_chunks();
+  sp->seg_chunks = seg_chunks;
+  const int64_t seglen = static_cast<int64_t>(seg_chunks) * SP_TE;
+  for (int b = 0; b < nb; ++b) {
+    segfirst[b] = static_cast<int32_t>(seg.size() / 3);
+    for (int64_t k = bs[b]; k < bs[b + 1]; k += seglen) {
+      seg.push_back(b);
+      seg.push_back(static_cast<int32_t>(k));
+      seg.push_back(static_cast<int32_t>(k + seglen < bs[b + 1] ? k + seglen : bs[b + 1]));
+    }
+  }
+  segfirst[nb] = static_cast<int32_t>(seg.size() / 3);
+  sp->nseg = segfirst[nb];
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&sp->d_seg), sizeof(int32_t) * (seg.size() + 3), st));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&sp->d_segfirst), sizeof(int32_t) * (nb + 1), st));
+  SB_TRY(pool_alloc(reinterpret_cast<void**>(&sp->d_segcur), sizeof(uint32_t) * ((static_cast<size_t>(sp->nseg) << sp->sh) + 4), st));
+  sp->bytes += sizeof(int32_t) * (seg.size() + nb + 1) + sizeof(uint32_t) * (static_cast<size_t>(sp->nseg) << sp->sh);
+  SB_CUDA(cudaMemcpyAsync(sp->d_seg, seg.data(), sizeof(int32_t) * seg.size(), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(sp->d_segfirst, segfirst.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  guard.armed = false;
+  *out = sp;
+  return SB200_OK;
+}
+
+int transpose_split_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double* d_x_out) {
+  cudaStream_t st = m->stream;
+  Trace tr(st);
+  tr.mark();
+  if (m->plan_split && (m->plan_split->sh != band_shift(m) || m->plan_split->seg_chunks != segment_chunks())) {
+    free_split_plan(m->plan_split, st);
+    m->plan_split = nullptr;
+  }
+  const bool cached = m->plan_split != nullptr;
+  if (!cached) SB_TRY(build_split_plan(m, &m->plan_split));
+  const SplitPlan* sp = m->plan_split;
+  tr.mark();
+  SB_CUDA(cudaMemcpyAsync(d_p_out, sp->d_rowptr, sizeof(int32_t) * (static_cast<size_t>(m->nrow) + 1), cudaMemcpyDeviceToDevice, st));
+  uint16_t* s_r = nullptr;
+  int32_t* s_c = nullptr;
+  double* s_x = nullptr;
+  const size_t n = static_cast<size_t>(m->nnz);
+  int rc = pool_alloc(reinterpret_cast<void**>(&s_r), padded_bytes(2 * n), st);
+  if (rc == SB200_OK) rc = pool_alloc(reinterpret_cast<void**>(&s_c), padded_bytes(4 * n), st);
+  if (rc == SB200_OK) rc = pool_alloc(reinterpret_cast<void**>(&s_x), padded_bytes(8 * n), st);
+  if (rc == SB200_OK) {
+    SplitArgs a;
+    memset(&a, 0, sizeof(a));
+    a.i = m->d_i;
+    a.p = m->d_p;
+    a.x = m->d_x;
+    a.s_r = s_r;
+    a.s_c = s_c;
+    a.s_x = s_x;
+    a.i_out = d_i_out;
+    a.x_out = d_x_out;
+    a.tb = sp->d_tb;
+    a.bstart = sp->d_bstart;
+    a.tilecol = sp->d_tilecol;
+    a.seg = sp->d_seg;
+    a.segcur = sp->d_segcur;
+    a.nseg = sp->nseg;
+    a.rowptr = sp->d_rowptr;
+    a.ntiles = sp->ntiles;
+    a.nnz = m->nnz;
+    a.nrow = m->nrow;
+    a.ncol = m->ncol;
+    a.sh = sp->sh;
+    a.nb = sp->nb;
+    cudaError_t e = cudaMemsetAsync(sp->d_counters, 0, sizeof(unsigned int) * 2, st);
+    if (e == cudaSuccess) {
+      a.keys = sp->nb;
+      a.kp = (a.keys + 7) & ~7;
+      a.kbits = key_bits(a.keys);
+      a.counter = sp->d_counters;
+      const size_t smem = split_smem_bytes<1>(a.kp);
+      auto kern = split_kernel<1>;
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e == cudaSuccess) {
+        const int per_sm = smem + 1024 <= 113 * 1024 ? 2 : 1;
+        int64_t grid = static_cast<int64_t>(m->sm_count) * per_sm;
+        if (grid > sp->ntiles) grid = sp->ntiles;
+        kern<<<static_cast<unsigned>(grid), SP_THREADS, smem, st>>>(a);
+        count_launch();
+        e = cudaGetLastError();
+      }
+    }
+    tr.mark();
+    if (e == cudaSuccess && !m->plan_split->segcur_ready && sp->nseg > 0) {
+      // first call: the cursors every segment starts from, counted from the record stream that now exists
+      const int R = 1 << sp->sh;
+      const int grid = sp->nseg < m->sm_count * 4 ? sp->nseg : m->sm_count * 4;
+      split_seg_hist_kernel<<<grid, SP_THREADS, sizeof(uint32_t) * R, st>>>(s_r, sp->d_seg, sp->nseg, sp->sh, sp->d_segcur);
+      split_seg_scan_kernel<<<static_cast<unsigned>((static_cast<int64_t>(m->nrow) + 255) / 256), 256, 0, st>>>(sp->d_segcur, sp->d_segfirst, sp->d_rowptr,
+                                                                                                          m->nrow, sp->sh);
+      count_launch(2);
+      e = cudaGetLastError();
+      if (e == cudaSuccess) m->plan_split->segcur_ready = true;
+    }
+    if (e == cudaSuccess) {
+      a.keys = 1 << sp->sh;
+      a.kp = (a.keys + 7) & ~7;
+      a.kbits = key_bits(a.keys);
+      a.counter = sp->d_counters + 1;
+      const size_t smem = split_smem_bytes<2>(a.kp);
+      auto kern = split_kernel<2>;
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e == cudaSuccess) {
+        const int per_sm = smem + 1024 <= 113 * 1024 ? 2 : 1;
+        int grid = m->sm_count * per_sm;
+        if (grid > sp->nseg) grid = sp->nseg;
+        if (grid < 1) grid = 1;
+        kern<<<grid, SP_THREADS, smem, st>>>(a);
+        count_launch();
+        e = cudaGetLastError();
+      }
+    }
+    tr.mark();
+    if (e != cudaSuccess) rc = cuda_fail(e, "transpose: stream split launch", __FILE__, __LINE__);
+  }
+  pool_free(s_r, st);
+  pool_free(s_c, st);
+  pool_free(s_x, st);
+  tr.report(sp, cached);
+  return rc;
+}
+
+}  // namespace sb200

@@ -178,9 +178,59 @@ def test_transpose_chunks_larger_than_the_image(bands, kcols, monkeypatch, check
         assert np.array_equal(tp, want[1]) and np.array_equal(ti, want[0]) and np.array_equal(bits(tx), bits(want[2])), path
 
 
+@pytest.mark.parametrize("shift", [None, "2", "7", "11"])
+def test_transpose_two_stream_splits_on_every_shape(synth_case, shift, monkeypatch, checker):
+    """The two-split transpose of tall matrices (transpose_split.cu) forced on every synthetic shape, with the band
+    width the library would pick and with forced ones (4, 128 and 2048 rows per band where the tables allow it):
+    bit-exact whatever the band width; the second call reuses the plan kept on the handle."""
+    name, spec, i, p, x = synth_case
+    monkeypatch.setenv("SB200_TRANSPOSE_PATH", "split")
+    if shift is not None:
+        if (spec.nrow >> int(shift)) >= 3072:
+            pytest.skip("more bands than the key table holds")
+        monkeypatch.setenv("SB200_SPLIT_SHIFT", shift)
+    wi, wp, wx = checker.transpose(i, p, x, spec.nrow, spec.ncol)
+    with DeviceMatrix.from_host(i, p, x, spec.nrow, spec.ncol) as D:
+        launches = []
+        for _ in range(2):
+            n0 = _lib.lib().sb200_launch_count()
+            ti, tp, tx = D.transpose_host()
+            launches.append(_lib.lib().sb200_launch_count() - n0)
+            assert np.array_equal(tp, wp) and np.array_equal(ti, wi) and np.array_equal(bits(tx), bits(wx)), (name, shift)
+        if len(x):
+            assert D.layouts() & 8 and launches[1] == 2, launches  # the two passes, nothing else, on a cached plan
+
+
+def test_transpose_two_stream_splits_hot_rows_and_short_columns(monkeypatch, checker):
+    """What the stable split must not trip over: a few rows holding most of the entries (thousands of equal keys in
+    one chunk), columns of length 0 and 1 between long ones (the column walk), a last tile of one entry."""
+    rng = np.random.default_rng(77)
+    nrow = 70_000
+    hot = np.array([5, 6, 40_000, 69_999])
+    lengths = list(rng.choice([0, 1, 2, 40, 3000], 5_000, p=[0.3, 0.3, 0.2, 0.15, 0.05]))
+    cols = []
+    for n in lengths:
+        rows = rng.choice(nrow, n, replace=False)
+        if n >= 2:
+            rows[:min(4, n)] = hot[:min(4, n)]
+        cols.append(np.unique(rows))
+    while (sum(len(c) for c in cols) % 4096) != 1:  # single-entry columns until the last tile holds one entry
+        cols.append(rng.integers(0, nrow, 1))
+    ncol = len(cols)
+    p = np.zeros(ncol + 1, np.int32)
+    p[1:] = np.cumsum([len(c) for c in cols])
+    i = np.concatenate(cols).astype(np.int32)
+    x = rng.standard_normal(len(i))
+    monkeypatch.setenv("SB200_TRANSPOSE_PATH", "split")
+    wi, wp, wx = checker.transpose(i, p, x, nrow, ncol)
+    with DeviceMatrix.from_host(i, p, x, nrow, ncol) as D:
+        ti, tp, tx = D.transpose_host()
+    assert np.array_equal(tp, wp) and np.array_equal(ti, wi) and np.array_equal(bits(tx), bits(wx))
+
+
 def test_transpose_golden_edges_on_both_paths(golden, monkeypatch):
     g = golden
-    for path in ("place", "banded"):
+    for path in ("place", "banded", "split"):
         monkeypatch.setenv("SB200_TRANSPOSE_PATH", path)
         with DeviceMatrix.from_host(g["i"], g["p"], g["x"], g["nrow"], g["ncol"]) as D:
             ti, tp, tx = D.transpose_host()
