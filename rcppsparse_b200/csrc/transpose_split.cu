@@ -74,6 +74,7 @@ __device__ __forceinline__ uint32_t ld_stream_u16(const uint16_t* p) {
   return v;
 }
 
+
 // ---- plan kernels -----------------------------------------------------------------------------------------------
 // Hc[b * ntiles + t] = entries of tile t in band b;  rowcnt[r] += 1 per entry
 __global__ void __launch_bounds__(SP_THREADS)
@@ -199,15 +200,15 @@ struct SplitArgs {
 };
 
 template <int PASS>
-size_t split_smem_bytes(int kp) {
-  return static_cast<size_t>(SP_TE) * (8 + 4 + 2 + (PASS == 1 ? 2 : 0)) + static_cast<size_t>(kp) * 4 * 3 +
-         static_cast<size_t>(SP_THREADS / 32) * kp * 2;
+size_t split_smem_bytes(int kp, int threads, int te) {
+  return static_cast<size_t>(te) * (8 + 4 + 2 + (PASS == 1 ? 2 : 0)) + static_cast<size_t>(kp) * 4 * 3 +
+         static_cast<size_t>(threads / 32) * kp * 2;
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(SP_THREADS, 2) split_kernel(const SplitArgs a) {
-  constexpr int THREADS = SP_THREADS, TE = SP_TE;
-  constexpr int W = THREADS / 32, EPT = TE / THREADS, SEG = EPT * 32;
+template <int PASS, int THREADS, int EPT>
+__global__ void __launch_bounds__(THREADS, (EPT > 8 ? 512 : 1024) / THREADS) split_kernel(const SplitArgs a) {
+  constexpr int TE = THREADS * EPT;
+  constexpr int W = THREADS / 32, SEG = EPT * 32;
   extern __shared__ __align__(16) unsigned char ssm[];
   __shared__ uint32_t wscan[W];
   __shared__ unsigned int s_unit;
@@ -296,18 +297,51 @@ __global__ void __launch_bounds__(SP_THREADS, 2) split_kernel(const SplitArgs a)
       }
     }
     // ---- rank inside the warp: equal keys of a step in lane order, steps in order ----------------------------------
-    // Which lanes hold my key: one ballot per key bit.  (match.any does this in one instruction, but with ~32 distinct
-    // keys per step — the normal case here — it held the XU pipe ~200 cycles per call and WAS the kernel's run time:
-    // profiles/r02/prof_split_v1_c2.summary.txt.)
+    // `same` = the lanes of this 32-record step that hold my key.  The general answer is one ballot per key bit (~45
+    // instructions a step; match.any is one instruction but no faster: profiles/r02/prof_split_v1_c2 vs _v2_c2), so
+    // each pass first tries what its input makes likely:
+    //   pass 1  a step inside ONE column has its rows ascending, so equal bands are adjacent: run heads by comparing
+    //           with the lane below, one ballot;
+    //   pass 2  a band's stream interleaves columns, rows look random: most steps have no two equal rows.  Every lane
+    //           leaves its lane id in a per-warp claim table (living in the image, idle until the placement) and reads
+    //           it back; nobody overwritten => every lane is alone.
+    uint8_t* claim = reinterpret_cast<uint8_t*>(ssm) + warp * KP;
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
       const bool valid = kr[j] != 0xffffffffu;
       const uint32_t key = kr[j] >> 16;
-      unsigned same = __ballot_sync(0xffffffffu, valid);
-      for (int b = 0; b < a.kbits; ++b) {
-        const bool bit = (key >> b) & 1u;
-        const unsigned bal = __ballot_sync(0xffffffffu, bit);
-        same &= bit ? bal : ~bal;
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      unsigned same;
+      bool fast;
+      if (PASS == 1) {
+        const int32_t c_first = __shfl_sync(0xffffffffu, cc[j], 0);
+        fast = __all_sync(0xffffffffu, !valid || cc[j] == c_first);
+      } else {
+        if (valid) claim[key] = static_cast<uint8_t>(lane);
+        __syncwarp();
+        fast = !__any_sync(0xffffffffu, valid && claim[key] != lane);
+      }
+      if (fast) {
+        if (PASS == 1) {
+          const uint32_t below = __shfl_up_sync(0xffffffffu, key, 1);
+          const unsigned heads = __ballot_sync(0xffffffffu, valid && (lane == 0 || key != below));
+          const int start = 31 - __clz(heads & (lt_mask | (1u << lane)));
+          const unsigned above = heads & ~(lt_mask | (1u << lane));
+          const int end = above ? __ffs(above) - 1 : __popc(vmask);  // valid lanes are a prefix of the step
+          same = (end >= 32 ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << start) - 1u);
+        } else {
+          same = 1u << lane;
+        }
+      } else {
+        same = vmask;
+        for (int b = 0; b < a.kbits; b += 4) {  // bits past kbits are 0 in every valid key: they change nothing
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const bool bit = (key >> (b + t)) & 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, bit);
+            same &= bit ? bal : ~bal;
+          }
+        }
       }
       uint16_t* slot = tbl + warp * KP + (valid ? key : 0u);
       const uint32_t old = *slot;  // every lane of the group reads, its lowest lane writes
@@ -428,6 +462,44 @@ __global__ void __launch_bounds__(SP_THREADS, 2) split_kernel(const SplitArgs a)
   }
 }
 
+
+// geometry: threads per CTA x records per thread.  512x8 (4096-record chunks, 2 CTAs per SM); SB200_SPLIT_CFG=1024x8 =
+// 8192-record chunks, one CTA per SM (measured within 10 % of each other, like 256x8 / 256x16 / 1024x4: profiles/r02)
+struct SplitCfg {
+  int threads, ept;
+};
+SplitCfg split_cfg() {
+  if (const char* e = getenv("SB200_SPLIT_CFG")) {
+    if (!strcmp(e, "1024x8")) return {1024, 8};
+  }
+  return {SP_THREADS, SP_TE / SP_THREADS};
+}
+
+template <int PASS, int THREADS, int EPT>
+cudaError_t launch_split(const SplitArgs& a, int sm_count, int64_t units, cudaStream_t st) {
+  const size_t smem = split_smem_bytes<PASS>(a.kp, THREADS, THREADS * EPT);
+  auto kern = split_kernel<PASS, THREADS, EPT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+  const int by_threads = (EPT > 8 ? 512 : 1024) / THREADS;
+  if (per_sm > by_threads) per_sm = by_threads;
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = static_cast<int64_t>(sm_count) * per_sm;
+  if (grid > units) grid = units;
+  if (grid < 1) grid = 1;
+  kern<<<static_cast<unsigned>(grid), THREADS, smem, st>>>(a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <int PASS>
+cudaError_t launch_split_cfg(const SplitArgs& a, int sm_count, int64_t units, cudaStream_t st) {
+  const SplitCfg c = split_cfg();
+  if (c.threads == 1024 && c.ept == 8) return launch_split<PASS, 1024, 8>(a, sm_count, units, st);
+  return launch_split<PASS, SP_THREADS, SP_TE / SP_THREADS>(a, sm_count, units, st);
+}
+
 struct Trace {  // SB200_TRACE=1: device time of the plan and of the two passes on stderr
   bool on;
   cudaStream_t st;
@@ -504,7 +576,10 @@ bool split_transpose_fits(const sb200_matrix* m) {
   const int64_t rb = static_cast<int64_t>(1) << sh;
   const int64_t nb = (m->nrow + rb - 1) >> sh;
   if (rb > SP_MAX_KEYS || nb > SP_MAX_KEYS) return false;
-  const int64_t ntiles = (m->nnz + SP_TE - 1) / SP_TE;
+  const int te_ = split_cfg().threads * split_cfg().ept;
+  const int64_t kmax = rb > nb ? rb : nb;
+  if (split_smem_bytes<1>(static_cast<int>((kmax + 7) & ~7), split_cfg().threads, te_) + 1024 > 227 * 1024) return false;
+  const int64_t ntiles = (m->nnz + te_ - 1) / te_;
   const size_t table = sizeof(int32_t) * static_cast<size_t>(nb) * static_cast<size_t>(ntiles);
   const size_t stream = 14ull * static_cast<size_t>(m->nnz);
   const size_t need = (m->plan_split ? 0 : 3 * table) + stream + (64ull << 20);
@@ -517,8 +592,8 @@ static int build_split_plan(sb200_matrix* m, SplitPlan** out) {
   if (!sp) return fail(SB200_E_NOMEM, "transpose: out of host memory");
   sp->sh = band_shift(m);
   sp->nb = static_cast<int>((static_cast<int64_t>(m->nrow) + (1 << sp->sh) - 1) >> sp->sh);
-  sp->te = SP_TE;
-  sp->ntiles = (m->nnz + SP_TE - 1) / SP_TE;
+  sp->te = split_cfg().threads * split_cfg().ept;
+  sp->ntiles = (m->nnz + sp->te - 1) / sp->te;
   const int nb = sp->nb;
   const int64_t nt = sp->ntiles, cells = static_cast<int64_t>(nb) * nt;
   uint32_t *d_hc = nullptr, *d_rowcnt = nullptr;
@@ -557,7 +632,7 @@ static int build_split_plan(sb200_matrix* m, SplitPlan** out) {
 
   SB_CUDA(cudaMemsetAsync(d_rowcnt, 0, sizeof(uint32_t) * static_cast<size_t>(m->nrow), st));
   int64_t grid = nt < static_cast<int64_t>(m->sm_count) * 4 ? nt : static_cast<int64_t>(m->sm_count) * 4;
-  split_hist_kernel<<<static_cast<unsigned>(grid), SP_THREADS, sizeof(uint32_t) * nb, st>>>(m->d_i, m->nnz, sp->sh, nb, SP_TE, nt, d_hc, d_rowcnt);
+  split_hist_kernel<<<static_cast<unsigned>(grid), SP_THREADS, sizeof(uint32_t) * nb, st>>>(m->d_i, m->nnz, sp->sh, nb, sp->te, nt, d_hc, d_rowcnt);
   count_launch();
   SB_CUDA(cudaGetLastError());
   SB_TRY(exclusive_scan_u32(st, d_rowcnt, sp->d_rowptr, m->nrow, nullptr, d_ws, ws_bytes));
@@ -568,7 +643,7 @@ static int build_split_plan(sb200_matrix* m, SplitPlan** out) {
     count_launch();
     SB_CUDA(cudaGetLastError());
   }
-  split_tilecol_kernel<<<static_cast<unsigned>((nt + 1 + 255) / 256), 256, 0, st>>>(m->d_p, m->ncol, m->nnz, SP_TE, nt, sp->d_tilecol);
+  split_tilecol_kernel<<<static_cast<unsigned>((nt + 1 + 255) / 256), 256, 0, st>>>(m->d_p, m->ncol, m->nnz, sp->te, nt, sp->d_tilecol);
   count_launch();
   SB_CUDA(cudaGetLastError());
   // pass-2 units: every band's stream in segments of SP_SEG_CHUNKS chunks
@@ -577,7 +652,7 @@ static int build_split_plan(sb200_matrix* m, SplitPlan** out) {
   SB_CUDA(cudaStreamSynchronize(st));
   const int seg_chunks = segment_chunks();
   sp->seg_chunks = seg_chunks;
-  const int64_t seglen = static_cast<int64_t>(seg_chunks) * SP_TE;
+  const int64_t seglen = static_cast<int64_t>(seg_chunks) * sp->te;
   for (int b = 0; b < nb; ++b) {
     segfirst[b] = static_cast<int32_t>(seg.size() / 3);
     for (int64_t k = bs[b]; k < bs[b + 1]; k += seglen) {
@@ -604,7 +679,8 @@ int transpose_split_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, 
   cudaStream_t st = m->stream;
   Trace tr(st);
   tr.mark();
-  if (m->plan_split && (m->plan_split->sh != band_shift(m) || m->plan_split->seg_chunks != segment_chunks())) {
+  if (m->plan_split && (m->plan_split->sh != band_shift(m) || m->plan_split->seg_chunks != segment_chunks() ||
+                        m->plan_split->te != split_cfg().threads * split_cfg().ept)) {
     free_split_plan(m->plan_split, st);
     m->plan_split = nullptr;
   }
@@ -650,17 +726,7 @@ int transpose_split_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, 
       a.kp = (a.keys + 7) & ~7;
       a.kbits = key_bits(a.keys);
       a.counter = sp->d_counters;
-      const size_t smem = split_smem_bytes<1>(a.kp);
-      auto kern = split_kernel<1>;
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (e == cudaSuccess) {
-        const int per_sm = smem + 1024 <= 113 * 1024 ? 2 : 1;
-        int64_t grid = static_cast<int64_t>(m->sm_count) * per_sm;
-        if (grid > sp->ntiles) grid = sp->ntiles;
-        kern<<<static_cast<unsigned>(grid), SP_THREADS, smem, st>>>(a);
-        count_launch();
-        e = cudaGetLastError();
-      }
+      e = launch_split_cfg<1>(a, m->sm_count, sp->ntiles, st);
     }
     tr.mark();
     if (e == cudaSuccess && !m->plan_split->segcur_ready && sp->nseg > 0) {
@@ -679,18 +745,7 @@ int transpose_split_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, 
       a.kp = (a.keys + 7) & ~7;
       a.kbits = key_bits(a.keys);
       a.counter = sp->d_counters + 1;
-      const size_t smem = split_smem_bytes<2>(a.kp);
-      auto kern = split_kernel<2>;
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (e == cudaSuccess) {
-        const int per_sm = smem + 1024 <= 113 * 1024 ? 2 : 1;
-        int grid = m->sm_count * per_sm;
-        if (grid > sp->nseg) grid = sp->nseg;
-        if (grid < 1) grid = 1;
-        kern<<<grid, SP_THREADS, smem, st>>>(a);
-        count_launch();
-        e = cudaGetLastError();
-      }
+      e = launch_split_cfg<2>(a, m->sm_count, sp->nseg, st);
     }
     tr.mark();
     if (e != cudaSuccess) rc = cuda_fail(e, "transpose: stream split launch", __FILE__, __LINE__);
