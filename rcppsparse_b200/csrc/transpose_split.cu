@@ -8,9 +8,9 @@
 //
 //   pass 1  the entry stream in storage (column-major) order is cut into tiles of 4096 entries; every tile is split,
 //           stably, by ROW BAND (band = row >> sh, ~sqrt(nrow) rows each) and appends its piece of each band to that
-//           band's stream.  Where the piece goes is structure only: first slot of (tile, band) = exclusive scan over
-//           (band major, tile minor) of the per-tile band counts — kept on the handle.  Record: row inside the band
-//           (16 bits), source column (32), value (64).
+//           band's stream (16-byte records).  Where the piece goes is structure only: first slot of (tile, band) = exclusive scan over
+//           (band major, tile minor) of the per-tile band counts — kept on the handle.  Record: value (64 bits),
+//           source column (32), row inside the band (32).
 //   pass 2  a band's stream is cut into segments of 4 chunks; a CTA takes a segment, walks it 4096 records at a time and
 //           splits each chunk, stably, by row; a row's piece is appended at the row's cursor (shared memory).  Where the
 //           cursors of a segment start is structure only too: p'[row] + the row's records in the band's earlier segments
@@ -25,8 +25,8 @@
 // inside a key = storage order in both passes => inside an output row = source column order: the canonical CSC of
 // A^T bit for bit, no sort, no global atomics.  No floating-point arithmetic.
 //
-// Roofline: HBM.  Algorithmic bytes 24N + 4(n+1) + 4(m+1); this path moves 12N + 14N + 14N + 12N plus
-// 4 bytes per (tile, band), so its ceiling is 0.46 of that roofline.
+// Roofline: HBM.  Algorithmic bytes 24N + 4(n+1) + 4(m+1); this path moves 12N + 16N + 16N + 12N plus
+// 4 bytes per (tile, band), so its ceiling is 0.43 of that roofline.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -68,10 +68,27 @@ constexpr int SP_TE = 4096;
 constexpr int SP_SEG_CHUNKS = 4;  // chunks per pass-2 unit (SB200_SPLIT_SEG)
 constexpr int SP_MAX_KEYS = 3072;  // bands, and rows per band: the (warp, key) table is 16 x keys x 2 bytes of shared memory
 
-__device__ __forceinline__ uint32_t ld_stream_u16(const uint16_t* p) {
-  uint16_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
-  return v;
+// One record of the band-major stream: value, source column, row inside the band — 16 bytes, so that a tile's piece of
+// a band is ONE contiguous run (three arrays meant three partial-sector pieces per (tile, band): 72 M at C2, and the
+// memory system takes ~50 G of those a second whatever the kernel does).
+struct __align__(16) Rec {
+  double x;
+  int32_t c;
+  uint32_t r;
+};
+__device__ __forceinline__ Rec ld_stream_rec(const Rec* p) {
+  uint32_t a, b, c, d;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+  Rec r;
+  r.x = __hiloint2double(static_cast<int>(b), static_cast<int>(a));
+  r.c = static_cast<int32_t>(c);
+  r.r = d;
+  return r;
+}
+__device__ __forceinline__ void st_rec(Rec* p, double x, int32_t c, uint32_t r) {
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(static_cast<uint32_t>(__double2loint(x))),
+               "r"(static_cast<uint32_t>(__double2hiint(x))), "r"(static_cast<uint32_t>(c)), "r"(r)
+               : "memory");
 }
 
 
@@ -143,14 +160,14 @@ __global__ void split_tilecol_kernel(const int32_t* __restrict__ gp, int32_t nco
 
 // h[(seg << sh) + r] = records of row r (inside its band) in segment seg of the record stream
 __global__ void __launch_bounds__(SP_THREADS)
-    split_seg_hist_kernel(const uint16_t* __restrict__ s_r, const int32_t* __restrict__ seg, int nseg, int sh, uint32_t* __restrict__ h) {
+    split_seg_hist_kernel(const Rec* __restrict__ rec, const int32_t* __restrict__ seg, int nseg, int sh, uint32_t* __restrict__ h) {
   extern __shared__ uint32_t hist[];
   const int R = 1 << sh;
   for (int u = blockIdx.x; u < nseg; u += gridDim.x) {
     for (int r = threadIdx.x; r < R; r += SP_THREADS) hist[r] = 0u;
     __syncthreads();
     const int64_t k0 = seg[3 * u + 1], k1 = seg[3 * u + 2];
-    for (int64_t k = k0 + threadIdx.x; k < k1; k += SP_THREADS) atomicAdd(&hist[ld_stream_u16(s_r + k)], 1u);
+    for (int64_t k = k0 + threadIdx.x; k < k1; k += SP_THREADS) atomicAdd(&hist[rec[k].r], 1u);
     __syncthreads();
     for (int r = threadIdx.x; r < R; r += SP_THREADS) h[(static_cast<int64_t>(u) << sh) + r] = hist[r];
     __syncthreads();
@@ -177,9 +194,7 @@ struct SplitArgs {
   const int32_t* i;  // pass 1 input: the mirror
   const int32_t* p;
   const double* x;
-  uint16_t* s_r;     // band-major record stream (pass 1 writes, pass 2 reads)
-  int32_t* s_c;
-  double* s_x;
+  Rec* rec;          // band-major record stream (pass 1 writes, pass 2 reads)
   int32_t* i_out;    // pass 2 output
   double* x_out;
   const int32_t* tb;
@@ -229,14 +244,15 @@ __global__ void __launch_bounds__(THREADS, (EPT > 8 ? 512 : 1024) / THREADS) spl
 
   for (int e = tid; e < tbl_vec; e += THREADS) reinterpret_cast<uint4*>(tbl)[e] = make_uint4(0u, 0u, 0u, 0u);
 
-  // one chunk: records [k0, k0 + n) of the input stream; cur[] holds every key's destination
-  auto chunk = [&](const int64_t k0, const int n, const int32_t tc0, const int32_t tc1, const int64_t next0, const int next_n) {
-    // ---- load: warp w owns records [w * SEG, (w + 1) * SEG), 32 consecutive ones per step -----------------------
-    uint32_t kr[EPT];  // key << 16 | row inside the band (pass 1)
-    uint32_t rk[EPT];  // rank inside (warp, key)
-    int32_t cc[EPT];
-    double xx[EPT];
-    const int seg0 = warp * SEG + lane;
+  // The records of the chunk in flight: warp w owns records [w * SEG, (w + 1) * SEG), 32 consecutive ones per step.
+  uint32_t kr[EPT];  // key << 16 | row inside the band (pass 1)
+  uint32_t rk[EPT];  // rank inside (warp, key)
+  int32_t cc[EPT];
+  double xx[EPT];
+  const int seg0 = warp * SEG + lane;
+
+  // records [k0, k0 + n) of unit u into the registers (pass 1: and their columns)
+  auto load = [&](const int64_t k0, const int n, const int64_t u) {
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
       const int q = seg0 + j * 32;
@@ -249,31 +265,17 @@ __global__ void __launch_bounds__(THREADS, (EPT > 8 ? 512 : 1024) / THREADS) spl
           kr[j] = (static_cast<uint32_t>(r >> a.sh) << 16) | static_cast<uint32_t>(r & ((1 << a.sh) - 1));
           xx[j] = ptx::ld_stream_f64(a.x + k0 + q);
         } else {
-          kr[j] = ld_stream_u16(a.s_r + k0 + q) << 16;
-          cc[j] = ptx::ld_stream_s32(a.s_c + k0 + q);
-          xx[j] = ptx::ld_stream_f64(a.s_x + k0 + q);
-        }
-      }
-    }
-    // the records this CTA takes next, on their way to L2 (one 128-byte line per thread and array)
-    if (next_n > 0) {
-      const int64_t e0 = next0 & ~int64_t(15);  // first record of the 128-byte line of doubles holding next0
-      const int64_t e = e0 + static_cast<int64_t>(tid) * 16;
-      if (e < next0 + next_n) {
-        if (PASS == 1) {
-          ptx::prefetch_l2(a.x + e);
-          if (!(tid & 1)) ptx::prefetch_l2(a.i + e);
-        } else {
-          ptx::prefetch_l2(a.s_x + e);
-          if (!(tid & 1)) ptx::prefetch_l2(a.s_c + e);
-          if (!(tid & 3)) ptx::prefetch_l2(a.s_r + e);
+          const Rec rc = ld_stream_rec(a.rec + k0 + q);
+          kr[j] = rc.r << 16;
+          cc[j] = rc.c;
+          xx[j] = rc.x;
         }
       }
     }
     if (PASS == 1 && seg0 < n) {
       // column of my first record by bisection inside the tile's columns, then walk: columns are long here
       const int64_t kf = k0 + seg0;
-      int32_t lo = tc0, hi = tc1;
+      int32_t lo = __ldg(a.tilecol + u), hi = __ldg(a.tilecol + u + 1);
       while (lo < hi) {
         const int32_t mid = lo + ((hi - lo + 1) >> 1);
         if (__ldg(a.p + mid) <= kf)
@@ -296,6 +298,66 @@ __global__ void __launch_bounds__(THREADS, (EPT > 8 ? 512 : 1024) / THREADS) spl
         }
       }
     }
+  };
+  // a unit's records: pass 1 one tile, pass 2 one segment of a band's stream
+  auto unit_bounds = [&](const int64_t u, int64_t& lo, int64_t& hi) {
+    if (PASS == 1) {
+      lo = u * TE;
+      hi = (a.nnz - lo < TE) ? a.nnz : lo + TE;
+    } else {
+      lo = __ldg(a.seg + 3 * u + 1);
+      hi = __ldg(a.seg + 3 * u + 2);
+    }
+  };
+  // where every key of unit u starts writing: fetched into registers early, stored to cur[] once the chunk in flight
+  // no longer needs it
+  constexpr int CPT = (SP_MAX_KEYS + THREADS - 1) / THREADS;
+  uint32_t curv[CPT];
+  auto fetch_cursors = [&](const int64_t u) {
+    const uint32_t* src = PASS == 1 ? reinterpret_cast<const uint32_t*>(a.tb) + u * a.nb : a.segcur + (u << a.sh);
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) {
+      const int key = tid + e * THREADS;
+      curv[e] = key < K ? __ldg(src + key) : 0u;
+    }
+  };
+  auto store_cursors = [&]() {
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) {
+      const int key = tid + e * THREADS;
+      if (key < K) cur[key] = curv[e];
+    }
+  };
+  // the records two chunks ahead, on their way to L2 (one 128-byte line per thread and array)
+  auto prefetch = [&](const int64_t k0, const int n) {
+    if (PASS == 1) {
+      const int64_t e = (k0 & ~int64_t(15)) + static_cast<int64_t>(tid) * 16;
+      if (e < k0 + n) {
+        ptx::prefetch_l2(a.x + e);
+        if (!(tid & 1)) ptx::prefetch_l2(a.i + e);
+      }
+    } else {
+      for (int64_t e = (k0 & ~int64_t(7)) + static_cast<int64_t>(tid) * 8; e < k0 + n; e += THREADS * 8) ptx::prefetch_l2(a.rec + e);
+    }
+  };
+
+  const int64_t units = PASS == 1 ? a.ntiles : static_cast<int64_t>(a.nseg);
+  if (tid == 0) s_unit = atomicAdd(a.counter, 1u);
+  __syncthreads();
+  int64_t u = s_unit;
+  if (u >= units) return;
+  int64_t k0, uend;
+  unit_bounds(u, k0, uend);
+  int n = static_cast<int>((uend - k0 < TE) ? uend - k0 : TE);
+  fetch_cursors(u);
+  store_cursors();
+  load(k0, n, u);
+  __syncthreads();  // s_unit read by everybody, the table clear, the cursors in place
+
+  // One chunk per turn.  The chunk after it is loaded into the registers the placement has just freed, so its global
+  // loads (pass 1: and the bisection for its columns) fly while the image is flushed; tickets are taken one unit ahead.
+  for (;;) {
+    const bool last_of_unit = k0 + n >= uend;
     // ---- rank inside the warp: equal keys of a step in lane order, steps in order ----------------------------------
     // `same` = the lanes of this 32-record step that hold my key.  The general answer is one ballot per key bit (~45
     // instructions a step; match.any is one instruction but no faster: profiles/r02/prof_split_v1_c2 vs _v2_c2), so
@@ -350,6 +412,7 @@ __global__ void __launch_bounds__(THREADS, (EPT > 8 ? 512 : 1024) / THREADS) spl
       rk[j] = old + __popc(same & lt_mask);
       __syncwarp();
     }
+    if (last_of_unit && tid == 0) s_unit = atomicAdd(a.counter, 1u);
     __syncthreads();
     // ---- per key: the warps' pieces in warp order; block scan over the keys -> image layout, destinations ----------
     // A thread owns 8 consecutive keys: their u16 counts are four 32-bit words, and no sum reaches 65536, so the
@@ -419,59 +482,59 @@ __global__ void __launch_bounds__(THREADS, (EPT > 8 ? 512 : 1024) / THREADS) spl
           img_k[pos] = static_cast<uint16_t>(key);
       }
     }
+    // ---- the chunk after this one -----------------------------------------------------------------------------------
+    int64_t nu = u, nk0 = k0 + TE, nuend = uend;
+    bool has_next = true;
+    if (last_of_unit) {
+      nu = s_unit;
+      has_next = nu < units;
+      if (has_next) unit_bounds(nu, nk0, nuend);
+    }
+    const int nn = has_next ? static_cast<int>((nuend - nk0 < TE) ? nuend - nk0 : TE) : 0;
+    if (has_next) {
+      load(nk0, nn, nu);
+      if (last_of_unit) fetch_cursors(nu);
+      if (PASS == 1) {
+        const int64_t pu = nu + gridDim.x;  // tickets go out in order: about where the tile after that will be
+        if (pu < units) prefetch(pu * TE, static_cast<int>((a.nnz - pu * TE < TE) ? a.nnz - pu * TE : TE));
+      } else if (nk0 + TE < nuend) {
+        prefetch(nk0 + TE, static_cast<int>((nuend - nk0 - TE < TE) ? nuend - nk0 - TE : TE));
+      }
+    }
     __syncthreads();
     // ---- flush: consecutive image slots of a key are consecutive global slots; clear the table ----------------------------
     for (int pp = tid; pp < n; pp += THREADS) {
       const uint32_t kw = PASS == 1 ? img_kr[pp] : static_cast<uint32_t>(img_k[pp]) << 16;
       const int64_t g = static_cast<int64_t>(static_cast<uint32_t>(gdelta[kw >> 16] + pp));
       if (PASS == 1) {
-        a.s_r[g] = static_cast<uint16_t>(kw & 0xffffu);
-        a.s_c[g] = img_c[pp];
-        a.s_x[g] = img_x[pp];
+        st_rec(a.rec + g, img_x[pp], img_c[pp], kw & 0xffffu);
       } else {
         a.i_out[g] = img_c[pp];
         a.x_out[g] = img_x[pp];
       }
     }
     for (int e = tid; e < tbl_vec; e += THREADS) reinterpret_cast<uint4*>(tbl)[e] = make_uint4(0u, 0u, 0u, 0u);
+    if (has_next && last_of_unit) store_cursors();
     __syncthreads();
-  };
-
-  for (;;) {
-    if (tid == 0) s_unit = atomicAdd(a.counter, 1u);
-    __syncthreads();  // also: the table is clear, the previous chunk's image has left
-    const int64_t u = s_unit;
-    if (PASS == 1) {
-      if (u >= a.ntiles) break;
-      const int64_t k0 = u * TE;
-      const int n = static_cast<int>((a.nnz - k0 < TE) ? a.nnz - k0 : TE);
-      for (int b = tid; b < K; b += THREADS) cur[b] = static_cast<uint32_t>(__ldg(a.tb + u * a.nb + b));
-      const int64_t un = u + gridDim.x;  // tickets go out in order: about where this CTA's next tile will be
-      const int64_t kn = un * TE;
-      chunk(k0, n, __ldg(a.tilecol + u), __ldg(a.tilecol + u + 1), kn, un < a.ntiles ? static_cast<int>((a.nnz - kn < TE) ? a.nnz - kn : TE) : 0);
-    } else {
-      if (u >= a.nseg) break;
-      const int R = 1 << a.sh;
-      const int64_t s0 = __ldg(a.seg + 3 * u + 1), s1 = __ldg(a.seg + 3 * u + 2);
-      for (int r = tid; r < R; r += THREADS) cur[r] = __ldg(a.segcur + (u << a.sh) + r);
-      for (int64_t k0 = s0; k0 < s1; k0 += TE) {
-        const int64_t kn = k0 + TE;
-        chunk(k0, static_cast<int>((s1 - k0 < TE) ? s1 - k0 : TE), 0, 0, kn, kn < s1 ? static_cast<int>((s1 - kn < TE) ? s1 - kn : TE) : 0);
-      }
-    }
+    if (!has_next) break;
+    u = nu;
+    k0 = nk0;
+    n = nn;
+    uend = nuend;
   }
 }
-
 
 // geometry: threads per CTA x records per thread.  512x8 (4096-record chunks, 2 CTAs per SM); SB200_SPLIT_CFG=1024x8 =
 // 8192-record chunks, one CTA per SM (measured within 10 % of each other, like 256x8 / 256x16 / 1024x4: profiles/r02)
 struct SplitCfg {
   int threads, ept;
 };
-SplitCfg split_cfg() {
-  if (const char* e = getenv("SB200_SPLIT_CFG")) {
+SplitCfg split_cfg(int pass = 1) {
+  if (const char* e = getenv(pass == 1 ? "SB200_SPLIT_CFG" : "SB200_SPLIT_CFG2")) {
     if (!strcmp(e, "1024x8")) return {1024, 8};
+    if (!strcmp(e, "512x8")) return {512, 8};
   }
+  if (pass == 2) return {1024, 8};  // twice the records per row and chunk: half the pieces on the way out (C2 1.55 -> 1.23 ms)
   return {SP_THREADS, SP_TE / SP_THREADS};
 }
 
@@ -495,7 +558,8 @@ cudaError_t launch_split(const SplitArgs& a, int sm_count, int64_t units, cudaSt
 
 template <int PASS>
 cudaError_t launch_split_cfg(const SplitArgs& a, int sm_count, int64_t units, cudaStream_t st) {
-  const SplitCfg c = split_cfg();
+  SplitCfg c = split_cfg(PASS);
+  if (split_smem_bytes<PASS>(a.kp, c.threads, c.threads * c.ept) + 1024 > 227 * 1024) c = {SP_THREADS, SP_TE / SP_THREADS};  // many keys: the small image
   if (c.threads == 1024 && c.ept == 8) return launch_split<PASS, 1024, 8>(a, sm_count, units, st);
   return launch_split<PASS, SP_THREADS, SP_TE / SP_THREADS>(a, sm_count, units, st);
 }
@@ -578,10 +642,10 @@ bool split_transpose_fits(const sb200_matrix* m) {
   if (rb > SP_MAX_KEYS || nb > SP_MAX_KEYS) return false;
   const int te_ = split_cfg().threads * split_cfg().ept;
   const int64_t kmax = rb > nb ? rb : nb;
-  if (split_smem_bytes<1>(static_cast<int>((kmax + 7) & ~7), split_cfg().threads, te_) + 1024 > 227 * 1024) return false;
+  if (split_smem_bytes<1>(static_cast<int>((kmax + 7) & ~7), SP_THREADS, SP_TE) + 1024 > 227 * 1024) return false;
   const int64_t ntiles = (m->nnz + te_ - 1) / te_;
   const size_t table = sizeof(int32_t) * static_cast<size_t>(nb) * static_cast<size_t>(ntiles);
-  const size_t stream = 14ull * static_cast<size_t>(m->nnz);
+  const size_t stream = sizeof(Rec) * static_cast<size_t>(m->nnz);
   const size_t need = (m->plan_split ? 0 : 3 * table) + stream + (64ull << 20);
   return device_free_bytes() > need + need / 8;
 }
@@ -689,22 +753,16 @@ int transpose_split_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, 
   const SplitPlan* sp = m->plan_split;
   tr.mark();
   SB_CUDA(cudaMemcpyAsync(d_p_out, sp->d_rowptr, sizeof(int32_t) * (static_cast<size_t>(m->nrow) + 1), cudaMemcpyDeviceToDevice, st));
-  uint16_t* s_r = nullptr;
-  int32_t* s_c = nullptr;
-  double* s_x = nullptr;
+  Rec* rec = nullptr;
   const size_t n = static_cast<size_t>(m->nnz);
-  int rc = pool_alloc(reinterpret_cast<void**>(&s_r), padded_bytes(2 * n), st);
-  if (rc == SB200_OK) rc = pool_alloc(reinterpret_cast<void**>(&s_c), padded_bytes(4 * n), st);
-  if (rc == SB200_OK) rc = pool_alloc(reinterpret_cast<void**>(&s_x), padded_bytes(8 * n), st);
+  int rc = pool_alloc(reinterpret_cast<void**>(&rec), padded_bytes(sizeof(Rec) * n), st);
   if (rc == SB200_OK) {
     SplitArgs a;
     memset(&a, 0, sizeof(a));
     a.i = m->d_i;
     a.p = m->d_p;
     a.x = m->d_x;
-    a.s_r = s_r;
-    a.s_c = s_c;
-    a.s_x = s_x;
+    a.rec = rec;
     a.i_out = d_i_out;
     a.x_out = d_x_out;
     a.tb = sp->d_tb;
@@ -733,7 +791,7 @@ int transpose_split_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, 
       // first call: the cursors every segment starts from, counted from the record stream that now exists
       const int R = 1 << sp->sh;
       const int grid = sp->nseg < m->sm_count * 4 ? sp->nseg : m->sm_count * 4;
-      split_seg_hist_kernel<<<grid, SP_THREADS, sizeof(uint32_t) * R, st>>>(s_r, sp->d_seg, sp->nseg, sp->sh, sp->d_segcur);
+      split_seg_hist_kernel<<<grid, SP_THREADS, sizeof(uint32_t) * R, st>>>(rec, sp->d_seg, sp->nseg, sp->sh, sp->d_segcur);
       split_seg_scan_kernel<<<static_cast<unsigned>((static_cast<int64_t>(m->nrow) + 255) / 256), 256, 0, st>>>(sp->d_segcur, sp->d_segfirst, sp->d_rowptr,
                                                                                                           m->nrow, sp->sh);
       count_launch(2);
@@ -750,9 +808,7 @@ int transpose_split_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, 
     tr.mark();
     if (e != cudaSuccess) rc = cuda_fail(e, "transpose: stream split launch", __FILE__, __LINE__);
   }
-  pool_free(s_r, st);
-  pool_free(s_c, st);
-  pool_free(s_x, st);
+  pool_free(rec, st);
   tr.report(sp, cached);
   return rc;
 }
