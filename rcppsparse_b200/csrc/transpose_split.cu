@@ -210,7 +210,6 @@ struct SplitArgs {
   int sh, nb;
   int keys;  // keys of this pass (bands / rows per band)
   int kp;    // table pitch: keys rounded up to a multiple of 8
-  int kbits; // bits that tell the keys apart
   unsigned int* counter;
 };
 
@@ -359,14 +358,15 @@ __global__ void __launch_bounds__(THREADS, (EPT > 8 ? 512 : 1024) / THREADS) spl
   for (;;) {
     const bool last_of_unit = k0 + n >= uend;
     // ---- rank inside the warp: equal keys of a step in lane order, steps in order ----------------------------------
-    // `same` = the lanes of this 32-record step that hold my key.  The general answer is one ballot per key bit (~45
-    // instructions a step; match.any is one instruction but no faster: profiles/r02/prof_split_v1_c2 vs _v2_c2), so
-    // each pass first tries what its input makes likely:
+    // `same` = the lanes of this 32-record step that hold my key.
     //   pass 1  a step inside ONE column has its rows ascending, so equal bands are adjacent: run heads by comparing
     //           with the lane below, one ballot;
-    //   pass 2  a band's stream interleaves columns, rows look random: most steps have no two equal rows.  Every lane
-    //           leaves its lane id in a per-warp claim table (living in the image, idle until the placement) and reads
-    //           it back; nobody overwritten => every lane is alone.
+    //   else    every lane leaves its lane id in a per-warp claim table indexed by key (it lives in the image, idle until
+    //           the placement) and reads it back: the lanes of one key all read the same survivor, a lane alone reads
+    //           itself.  Nobody overwritten => every lane is alone (most steps of pass 2: a band's stream interleaves
+    //           columns, rows look random); otherwise the groups are the lanes with equal survivors — five ballots, one
+    //           per bit of a lane id.  (One ballot per KEY bit was ~45 instructions per record at 1024 keys; match.any is
+    //           one instruction and no faster: profiles/r02/prof_split_v1_c2 vs _v2_c2.)
     uint8_t* claim = reinterpret_cast<uint8_t*>(ssm) + warp * KP;
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
@@ -374,32 +374,29 @@ __global__ void __launch_bounds__(THREADS, (EPT > 8 ? 512 : 1024) / THREADS) spl
       const uint32_t key = kr[j] >> 16;
       const unsigned vmask = __ballot_sync(0xffffffffu, valid);
       unsigned same;
-      bool fast;
+      bool runs = false;
       if (PASS == 1) {
         const int32_t c_first = __shfl_sync(0xffffffffu, cc[j], 0);
-        fast = __all_sync(0xffffffffu, !valid || cc[j] == c_first);
+        runs = __all_sync(0xffffffffu, !valid || cc[j] == c_first);
+      }
+      if (runs) {
+        const uint32_t below = __shfl_up_sync(0xffffffffu, key, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, valid && (lane == 0 || key != below));
+        const int start = 31 - __clz(heads & (lt_mask | (1u << lane)));
+        const unsigned above = heads & ~(lt_mask | (1u << lane));
+        const int end = above ? __ffs(above) - 1 : __popc(vmask);  // valid lanes are a prefix of the step
+        same = (end >= 32 ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << start) - 1u);
       } else {
         if (valid) claim[key] = static_cast<uint8_t>(lane);
         __syncwarp();
-        fast = !__any_sync(0xffffffffu, valid && claim[key] != lane);
-      }
-      if (fast) {
-        if (PASS == 1) {
-          const uint32_t below = __shfl_up_sync(0xffffffffu, key, 1);
-          const unsigned heads = __ballot_sync(0xffffffffu, valid && (lane == 0 || key != below));
-          const int start = 31 - __clz(heads & (lt_mask | (1u << lane)));
-          const unsigned above = heads & ~(lt_mask | (1u << lane));
-          const int end = above ? __ffs(above) - 1 : __popc(vmask);  // valid lanes are a prefix of the step
-          same = (end >= 32 ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << start) - 1u);
-        } else {
+        const uint32_t who = valid ? claim[key] : static_cast<uint32_t>(lane);
+        if (!__any_sync(0xffffffffu, who != static_cast<uint32_t>(lane))) {
           same = 1u << lane;
-        }
-      } else {
-        same = vmask;
-        for (int b = 0; b < a.kbits; b += 4) {  // bits past kbits are 0 in every valid key: they change nothing
+        } else {
+          same = vmask;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const bool bit = (key >> (b + t)) & 1u;
+          for (int b = 0; b < 5; ++b) {
+            const bool bit = (who >> b) & 1u;
             const unsigned bal = __ballot_sync(0xffffffffu, bit);
             same &= bit ? bal : ~bal;
           }
@@ -591,12 +588,6 @@ struct Trace {  // SB200_TRACE=1: device time of the plan and of the two passes 
   }
 };
 
-int key_bits(int keys) {
-  int b = 0;
-  while ((1 << b) < keys) ++b;
-  return b;
-}
-
 int segment_chunks() {
   if (const char* e = getenv("SB200_SPLIT_SEG")) {
     const int v = atoi(e);
@@ -608,6 +599,7 @@ int segment_chunks() {
 int band_shift(const sb200_matrix* m) {
   int sh = 0;
   while ((static_cast<int64_t>(1) << (2 * sh)) < m->nrow) ++sh;  // 2^sh >= sqrt(nrow): bands ~ rows per band
+  while ((1 << sh) > SP_MAX_KEYS) --sh;                          // beyond 2^22 rows: 2048 rows a band, up to 3072 bands
   if (const char* e = getenv("SB200_SPLIT_SHIFT")) {
     const int v = atoi(e);
     if (v >= 0 && v <= 16) sh = v;
@@ -782,7 +774,6 @@ int transpose_split_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, 
     if (e == cudaSuccess) {
       a.keys = sp->nb;
       a.kp = (a.keys + 7) & ~7;
-      a.kbits = key_bits(a.keys);
       a.counter = sp->d_counters;
       e = launch_split_cfg<1>(a, m->sm_count, sp->ntiles, st);
     }
@@ -801,7 +792,6 @@ int transpose_split_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, 
     if (e == cudaSuccess) {
       a.keys = 1 << sp->sh;
       a.kp = (a.keys + 7) & ~7;
-      a.kbits = key_bits(a.keys);
       a.counter = sp->d_counters + 1;
       e = launch_split_cfg<2>(a, m->sm_count, sp->nseg, st);
     }
