@@ -150,7 +150,8 @@ int sb200_matrix_band_companion(sb200_matrix* m, int which, int action);
 /* Bit mask of the cached layouts this mirror holds: 1 row-ordered copy, 2 band-major companion (A^T v),
  * 4 band-major companion of the row-ordered copy (A v), 8 transpose plan. */
 int sb200_matrix_layouts(sb200_matrix* m, int* mask);
-/* HBM bytes the cached layouts of this mirror occupy (row-ordered copy + band-major companions), beside its i/p/x. */
+/* HBM bytes the cached layouts of this mirror occupy (row-ordered copy, band-major companions, transpose plan),
+ * beside its i/p/x. */
 int sb200_matrix_layout_bytes(sb200_matrix* m, int64_t* bytes);
 
 /* ---- cross-GPU exchange for column-sharded matrices (one process per GPU, GPUs of one node) ---------

@@ -10,6 +10,7 @@
 #include <new>
 #include <string>
 
+#include "bandplan.cuh"
 #include "common.cuh"
 
 namespace sb200 {
@@ -719,6 +720,13 @@ int sb200_matrix_layout_bytes(sb200_matrix* m, int64_t* bytes) {
   if (m->rows_state == 1 && m->rows) {
     total += 12 * m->rows->nnz + 4 * (static_cast<int64_t>(m->rows->ncol) + 1);  // row-ordered copy: x', i', p'
     total += band_companion_bytes(m->rows);
+  }
+  // transpose plans kept between calls (structure only): band pointers + per-(row, split) offsets, or the destination
+  // tables of the two stream splits
+  total += split_plan_bytes(m->plan_split);
+  if (const BandPlan* bp = m->plan_transpose) {
+    total += 4 * (static_cast<int64_t>(bp->nb > 0 ? bp->nb - 1 : 0) * m->ncol + static_cast<int64_t>(m->nrow) * bp->S + 1 + bp->nb + 1 + bp->S + 1);
+    if (bp->S > 1) total += 4 * (static_cast<int64_t>(m->nrow) + 1);
   }
   *bytes = total;
   return SB200_OK;
