@@ -8,22 +8,23 @@
 //
 //   pass 1  the entry stream in storage (column-major) order is cut into tiles of 4096 entries; every tile is split,
 //           stably, by ROW BAND (band = row >> sh, ~sqrt(nrow) rows each) and appends its piece of each band to that
-//           band's stream (16-byte records).  Where the piece goes is structure only: first slot of (tile, band) = exclusive scan over
-//           (band major, tile minor) of the per-tile band counts — kept on the handle.  Record: value (64 bits),
-//           source column (32), row inside the band (32).
-//   pass 2  a band's stream is cut into segments of 4 chunks; a CTA takes a segment, walks it 4096 records at a time and
+//           band's stream of 16-byte records (value, source column, row inside the band).  Where the piece goes is
+//           structure only: first slot of (tile, band) = exclusive scan over (band major, tile minor) of the per-tile
+//           band counts — kept on the handle.
+//   pass 2  a band's stream is cut into segments of 4 chunks; a CTA takes a segment, walks it 8192 records at a time and
 //           splits each chunk, stably, by row; a row's piece is appended at the row's cursor (shared memory).  Where the
 //           cursors of a segment start is structure only too: p'[row] + the row's records in the band's earlier segments
 //           (counted once, on the first call, from the record stream pass 1 has just written; kept on the handle).
 //
 // Both passes are the same kernel (split_kernel<PASS>).  The stable split of a chunk: warp w owns the w-th contiguous
-// 256 records; one ballot per key bit tells a lane which lanes of its 32-record step hold the same key (rank in lane =
-// storage order); a table of counts per
-// (warp, key) in shared memory — u16, touched by the key's lowest lane only — carries the rank across the steps of
-// a warp; one scan per key over the 16 warps and one block scan over the keys lay the chunk out key-major in a
-// shared-memory IMAGE; the image leaves linearly, so the records of one key are consecutive global stores.  Order
-// inside a key = storage order in both passes => inside an output row = source column order: the canonical CSC of
-// A^T bit for bit, no sort, no global atomics.  No floating-point arithmetic.
+// 256 records; every lane learns which lanes of its 32-record step hold the same key (run heads inside one column in
+// pass 1; a per-warp claim table otherwise — see the kernel); a table of counts per (warp, key) in shared memory — u16,
+// written by a group's lowest lane only — carries the rank across the steps of a warp; one scan per key over the warps
+// and one block scan over the keys lay the chunk out key-major in a shared-memory IMAGE; the image leaves linearly, so
+// the records of one key are consecutive global stores.  Order inside a key = storage order in both passes => inside an
+// output row = source column order: the canonical CSC of A^T bit for bit, no sort, no global atomics.  No
+// floating-point arithmetic.  Both passes run one chunk ahead (next chunk's records in the registers the placement has
+// freed, its cursors fetched, the chunk after that on its way to L2) while the image is flushed.
 //
 // Roofline: HBM.  Algorithmic bytes 24N + 4(n+1) + 4(m+1); this path moves 12N + 16N + 16N + 12N plus
 // 4 bytes per (tile, band), so its ceiling is 0.43 of that roofline.
@@ -198,15 +199,12 @@ struct SplitArgs {
   int32_t* i_out;    // pass 2 output
   double* x_out;
   const int32_t* tb;
-  const int32_t* bstart;
   const int32_t* tilecol;
   const int32_t* seg;
   const uint32_t* segcur;
   int nseg;
-  const int32_t* rowptr;
   int64_t ntiles;
   int64_t nnz;
-  int32_t nrow, ncol;
   int sh, nb;
   int keys;  // keys of this pass (bands / rows per band)
   int kp;    // table pitch: keys rounded up to a multiple of 8
@@ -758,16 +756,12 @@ int transpose_split_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, 
     a.i_out = d_i_out;
     a.x_out = d_x_out;
     a.tb = sp->d_tb;
-    a.bstart = sp->d_bstart;
     a.tilecol = sp->d_tilecol;
     a.seg = sp->d_seg;
     a.segcur = sp->d_segcur;
     a.nseg = sp->nseg;
-    a.rowptr = sp->d_rowptr;
     a.ntiles = sp->ntiles;
     a.nnz = m->nnz;
-    a.nrow = m->nrow;
-    a.ncol = m->ncol;
     a.sh = sp->sh;
     a.nb = sp->nb;
     cudaError_t e = cudaMemsetAsync(sp->d_counters, 0, sizeof(unsigned int) * 2, st);
