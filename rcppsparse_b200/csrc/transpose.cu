@@ -612,8 +612,13 @@ int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double
   }
   PhaseTimer tr(st);
   tr.mark();
-  const int kind = transpose_kind(m);
-  if (kind == 3) return transpose_split_device(m, d_p_out, d_i_out, d_x_out);
+  int kind = transpose_kind(m);
+  if (kind == 3) {
+    const int rc3 = transpose_split_device(m, d_p_out, d_i_out, d_x_out);
+    if (rc3 != SB200_E_NOMEM) return rc3;
+    cudaGetLastError();  // no room for the tables or the record stream after all: the banded kernel needs neither
+    kind = 1;
+  }
   int env_bands = 0, env_splits = 0;
   if (const char* e = getenv("SB200_TRANSPOSE_SPLITS")) env_splits = atoi(e);
   if (const char* e = getenv("SB200_TRANSPOSE_BANDS")) env_bands = atoi(e);
