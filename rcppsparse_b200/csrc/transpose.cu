@@ -585,17 +585,20 @@ struct PhaseTimer {  // SB200_TRACE=1: device time of the plan and of the placem
 // kind: 1 = banded two-pass kernel of bands.cu (2432-row bands), 2 = chunk-sort placement (384-row bands),
 // 3 = two stable stream splits (transpose_split.cu).  Tall matrices — too few entries per (column, 384-row band) for the
 // chunk sort — take 3 when its tables fit, else 1.
-static int transpose_kind(const sb200_matrix* m) {
+static int transpose_kind(const sb200_matrix* m, bool allow_split = true) {
   if (const char* e = getenv("SB200_TRANSPOSE_PATH")) {
     if (!strcmp(e, "banded") || !strcmp(e, "1")) return 1;
     if (!strcmp(e, "place") || !strcmp(e, "2")) return 2;
-    if ((!strcmp(e, "split") || !strcmp(e, "3")) && split_transpose_fits(m)) return 3;
+    if ((!strcmp(e, "split") || !strcmp(e, "3")) && allow_split && split_transpose_fits(m)) return 3;
   }
-  // bands needed so that none exceeds 384 rows vs. bands that still leave ~2 entries per (column, band) run
-  const double floor_bands = static_cast<double>(m->nrow) / (0.9 * PL_ROWS_CAP);
-  const double by_density = static_cast<double>(m->nnz) / (2.0 * static_cast<double>(m->ncol > 0 ? m->ncol : 1));
-  if (floor_bands <= by_density) return 2;
-  return split_transpose_fits(m) ? 3 : 1;
+  // Mean run of a column inside a 384-row band decides (measured, profiles/r02/opbench_crossover.jsonl): with runs of a
+  // dozen entries and more (C3) the chunk sort's single pass wins; below that the two-split path does — by 1.3x at ~7
+  // entries a run, 3x at ~2 — unless the matrix is so small that two more launches and their tables are what it costs.
+  const double bands384 = static_cast<double>(m->nrow) / (0.9 * PL_ROWS_CAP) + 1.0;
+  const double mean_run = static_cast<double>(m->nnz) / (static_cast<double>(m->ncol > 0 ? m->ncol : 1) * bands384);
+  if (mean_run >= 12.0 || (m->nnz < 8000000 && mean_run >= 2.0)) return 2;
+  if (allow_split && split_transpose_fits(m)) return 3;
+  return mean_run >= 2.0 ? 2 : 1;
 }
 
 int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double* d_x_out) {
@@ -616,8 +619,8 @@ int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double
   if (kind == 3) {
     const int rc3 = transpose_split_device(m, d_p_out, d_i_out, d_x_out);
     if (rc3 != SB200_E_NOMEM) return rc3;
-    cudaGetLastError();  // no room for the tables or the record stream after all: the banded kernel needs neither
-    kind = 1;
+    cudaGetLastError();  // no room for the tables or the record stream after all: the single-pass kernels need neither
+    kind = transpose_kind(m, false);
   }
   int env_bands = 0, env_splits = 0;
   if (const char* e = getenv("SB200_TRANSPOSE_SPLITS")) env_splits = atoi(e);
