@@ -211,6 +211,47 @@ struct SplitArgs {
   unsigned int* counter;
 };
 
+
+// Exclusive scan over the warps of the (warp, key) counts of WPT words (two u16 keys each) of one thread, in place;
+// tot receives the totals.  Eight words are in flight before the first store.
+template <int WPT, int W>
+__device__ __forceinline__ void scan_warps(uint32_t* col, const int pitch, uint32_t (&tot)[4]) {
+  constexpr int B = 8 / WPT;  // warps per batch: eight words in flight before the first store
+#pragma unroll
+  for (int w0 = 0; w0 < W; w0 += B) {
+    uint32_t c[B][WPT];
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+      const uint32_t* src = col + (w0 + i) * pitch;
+      if (WPT == 1) {
+        c[i][0] = src[0];
+      } else if (WPT == 2) {
+        const uint2 v = *reinterpret_cast<const uint2*>(src);
+        c[i][0] = v.x;
+        c[i][WPT - 1] = v.y;
+      } else {
+        const uint4 v = *reinterpret_cast<const uint4*>(src);
+        c[i][0] = v.x;
+        c[i][1 % WPT] = v.y;
+        c[i][2 % WPT] = v.z;
+        c[i][3 % WPT] = v.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+      uint32_t* dst = col + (w0 + i) * pitch;
+      if (WPT == 1)
+        dst[0] = tot[0];
+      else if (WPT == 2)
+        *reinterpret_cast<uint2*>(dst) = make_uint2(tot[0], tot[1]);
+      else
+        *reinterpret_cast<uint4*>(dst) = make_uint4(tot[0], tot[1], tot[2], tot[3]);
+#pragma unroll
+      for (int q = 0; q < WPT; ++q) tot[q] += c[i][q];
+    }
+  }
+}
+
 template <int PASS>
 size_t split_smem_bytes(int kp, int threads, int te) {
   return static_cast<size_t>(te) * (8 + 4 + 2 + (PASS == 1 ? 2 : 0)) + static_cast<size_t>(kp) * 4 * 3 +
@@ -410,25 +451,25 @@ __global__ void __launch_bounds__(THREADS, (EPT > 8 ? 512 : 1024) / THREADS) spl
     if (last_of_unit && tid == 0) s_unit = atomicAdd(a.counter, 1u);
     __syncthreads();
     // ---- per key: the warps' pieces in warp order; block scan over the keys -> image layout, destinations ----------
-    // A thread owns 8 consecutive keys: their u16 counts are four 32-bit words, and no sum reaches 65536, so the
-    // scan over the warps is four plain adds per warp.
+    // A thread owns 2, 4 or 8 consecutive keys (as few as still covers all keys with one thread each: the scan over the
+    // warps is a dependent chain, so the more threads share it the shorter the wait of everybody else).  Two u16 counts
+    // are one 32-bit word and no sum reaches 65536, so the scan is one plain add per word and warp; eight words are
+    // loaded before the first store.
     uint32_t mytot = 0;
-    uint4 tot4 = make_uint4(0u, 0u, 0u, 0u);
-    const bool owner = tid * 8 < KP;
+    uint32_t totw[4] = {0u, 0u, 0u, 0u};
+    const int wpt = (KP <= 2 * THREADS) ? 1 : (KP <= 4 * THREADS) ? 2 : 4;  // words per owner thread
+    const bool owner = tid * 2 * wpt < KP;
     if (owner) {
-      uint4* col = reinterpret_cast<uint4*>(tbl + tid * 8);
-      const int pitch = KP / 8;
+      uint32_t* col = reinterpret_cast<uint32_t*>(tbl) + tid * wpt;
+      const int pitch = KP / 2;
+      if (wpt == 1)
+        scan_warps<1, W>(col, pitch, totw);
+      else if (wpt == 2)
+        scan_warps<2, W>(col, pitch, totw);
+      else
+        scan_warps<4, W>(col, pitch, totw);
 #pragma unroll
-      for (int w = 0; w < W; ++w) {
-        const uint4 c = col[w * pitch];
-        col[w * pitch] = tot4;
-        tot4.x += c.x;
-        tot4.y += c.y;
-        tot4.z += c.z;
-        tot4.w += c.w;
-      }
-      mytot = (tot4.x & 0xffffu) + (tot4.x >> 16) + (tot4.y & 0xffffu) + (tot4.y >> 16) + (tot4.z & 0xffffu) + (tot4.z >> 16) +
-              (tot4.w & 0xffffu) + (tot4.w >> 16);
+      for (int q = 0; q < 4; ++q) mytot += (totw[q] & 0xffffu) + (totw[q] >> 16);
     }
     uint32_t incl = mytot;
 #pragma unroll
@@ -443,23 +484,21 @@ __global__ void __launch_bounds__(THREADS, (EPT > 8 ? 512 : 1024) / THREADS) spl
 #pragma unroll
       for (int w = 0; w < W; ++w)
         if (w < warp) base += wscan[w];
-      const uint32_t t8[8] = {tot4.x & 0xffffu, tot4.x >> 16, tot4.y & 0xffffu, tot4.y >> 16,
-                              tot4.z & 0xffffu, tot4.z >> 16, tot4.w & 0xffffu, tot4.w >> 16};
-      uint32_t kb[8], c0[8];
-      *reinterpret_cast<uint4*>(c0) = *reinterpret_cast<const uint4*>(cur + tid * 8);
-      *reinterpret_cast<uint4*>(c0 + 4) = *reinterpret_cast<const uint4*>(cur + tid * 8 + 4);
+      const int key0 = tid * 2 * wpt;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        kb[e] = base;
-        base += t8[e];
-      }
-      *reinterpret_cast<uint4*>(kbase + tid * 8) = make_uint4(kb[0], kb[1], kb[2], kb[3]);
-      *reinterpret_cast<uint4*>(kbase + tid * 8 + 4) = make_uint4(kb[4], kb[5], kb[6], kb[7]);
-      *reinterpret_cast<uint4*>(gdelta + tid * 8) = make_uint4(c0[0] - kb[0], c0[1] - kb[1], c0[2] - kb[2], c0[3] - kb[3]);
-      *reinterpret_cast<uint4*>(gdelta + tid * 8 + 4) = make_uint4(c0[4] - kb[4], c0[5] - kb[5], c0[6] - kb[6], c0[7] - kb[7]);
-      if (PASS == 2) {
-        *reinterpret_cast<uint4*>(cur + tid * 8) = make_uint4(c0[0] + t8[0], c0[1] + t8[1], c0[2] + t8[2], c0[3] + t8[3]);
-        *reinterpret_cast<uint4*>(cur + tid * 8 + 4) = make_uint4(c0[4] + t8[4], c0[5] + t8[5], c0[6] + t8[6], c0[7] + t8[7]);
+      for (int q = 0; q < 4; ++q) {
+        if (q < wpt) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int key = key0 + 2 * q + h;
+            const uint32_t tot = h ? (totw[q] >> 16) : (totw[q] & 0xffffu);
+            const uint32_t c0 = cur[key];
+            kbase[key] = base;
+            gdelta[key] = static_cast<int32_t>(c0 - base);
+            if (PASS == 2) cur[key] = c0 + tot;
+            base += tot;
+          }
+        }
       }
     }
     __syncthreads();
