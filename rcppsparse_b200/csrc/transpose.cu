@@ -593,11 +593,11 @@ static int transpose_kind(const sb200_matrix* m, bool allow_split = true) {
   }
   // Mean run of a column inside a 384-row band decides (measured, profiles/r02/opbench_crossover.jsonl): with runs of a
   // dozen entries and more (C3) the chunk sort's single pass wins; below that the two-split path does — by 1.3x at ~7
-  // entries a run, 3x at ~2 — unless the matrix is so small that two more launches and their tables are what it costs.
+  // entries a run, 3x at ~2 — unless the matrix is so small that two more launches and their ~1000-key tables are what it costs.
   const double bands384 = static_cast<double>(m->nrow) / (0.9 * PL_ROWS_CAP) + 1.0;
   const double mean_run = static_cast<double>(m->nnz) / (static_cast<double>(m->ncol > 0 ? m->ncol : 1) * bands384);
   if (mean_run >= 12.0 || (m->nnz < 8000000 && mean_run >= 2.0)) return 2;
-  if (allow_split && split_transpose_fits(m)) return 3;
+  if (m->nnz >= 4000000 && allow_split && split_transpose_fits(m)) return 3;  // 1e6 entries over 1e6 rows: 1.2 ms split, 0.33 banded
   return mean_run >= 2.0 ? 2 : 1;
 }
 
