@@ -241,6 +241,19 @@ def test_transpose_five_million_rows(checker, monkeypatch):
     assert np.array_equal(tp, wp) and np.array_equal(ti, wi) and np.array_equal(bits(tx), bits(wx))
 
 
+def test_transpose_fuzz_every_path(monkeypatch):
+    """tools/transpose_fuzz.py: random shapes (1 .. 4e6 rows, 1 .. 5e4 columns, uniform and power-law, empty columns,
+    row popularity levels) through the two-split path (library's and a random band width), the chunk sort, the banded
+    kernel and the library's own choice, twice each (second call on the cached plan), bit for bit against the oracle."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "transpose_fuzz.py"), "16", "5"], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and "bit-exact" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_transpose_golden_edges_on_both_paths(golden, monkeypatch):
     g = golden
     for path in ("place", "banded", "split"):
