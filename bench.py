@@ -15,7 +15,8 @@ sweep of the next step); every result of every timed step is complete before the
 
 The other three hot ops run on THEIR OWN BASELINE configs in the same run and are reported in
 `roofline_by_op` next to the C2 reductions (same K/W, CUDA events on the launching stream, inputs >> L2):
-  * transpose (RcppSparse.h:375-385) on C3, 30k x 1M power-law columns + row popularity, ~1.5e9 entries (N = 1);
+  * transpose (RcppSparse.h:375-385) on C3, 30k x 1M power-law columns + row popularity, ~1.5e9 entries (N = 1), and — the
+    other transpose path, two stream splits — on the tall C2 and C4 (`transpose@C2`, `transpose@C4`);
   * A v and A^T v (iterator idiom, shapes of RcppSparse.h:140-142 / 133-135) on C4, 2^20 x 2M power-law columns,
     ~2.0e9 entries — at N > 1 the SAME matrix split into nnz-balanced column blocks (strong scaling; `c4_strong`
     carries per-op times, the NVLink term and, measured in the same run on rank 0's GPU, the one-GPU time).
@@ -378,13 +379,21 @@ def in_run_parity(ctx, args):
             "worst_err_over_sum_abs_terms": worst, "layouts": "first-call kernels and cached layouts both checked"}
 
 
-def section_transpose(ctx, args, peak, steps, warmup):
-    """CSC -> CSR transpose on C3 (BASELINE configs[2]) on this rank's GPU: sb200_transpose_dev, result kept in HBM."""
+TRANSPOSE_KERNELS = {"C3": "transpose_bitrank_kernel", "C2": "split_kernel<1> + split_kernel<2>", "C4": "split_kernel<1> + split_kernel<2>"}
+
+
+def section_transpose(ctx, args, peak, steps, warmup, cfg="C3"):
+    """CSC -> CSR transpose on C3 (BASELINE configs[2]) — or on the tall C2 / C4, which take the two-split path — on this
+    rank's GPU: sb200_transpose_dev, result kept in HBM."""
     import torch
 
     from rcppsparse_b200 import DeviceMatrix, synth
 
-    spec = synth.config("C3", args.scale)
+    spec = synth.config(cfg, args.scale)
+    # every call allocates its result (12 B/entry) from the library's pool; start from an empty pool so that the blocks a
+    # previous section left behind (other sizes) do not push the allocator onto its slow paths mid-measurement
+    from rcppsparse_b200 import _lib
+    _lib.lib().sb200_trim(ctx.local_rank)
     t0 = time.perf_counter()
     D = DeviceMatrix.synth(spec, device=ctx.local_rank)
     D.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -392,16 +401,29 @@ def section_transpose(ctx, args, peak, steps, warmup):
     gen_s = time.perf_counter() - t0
     keep = []
 
-    def run():
+    def run_alloc():
         keep.clear()  # the previous result goes back to the pool before the next one is allocated
         keep.append(D.transpose_dev())
 
+    def run():
+        D.transpose_into(keep[0])  # the same transpose into the result that exists: no allocation, same kernels
+
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    run()
+    run_alloc()
     e1.record()
     torch.cuda.synchronize()
     first_ms = e0.elapsed_time(e1)
+    # the allocating form (what Matrix::transpose() is): median over a few calls — multi-GB blocks going through the
+    # pool every call show up as occasional allocator spikes of 0.1-1 s at C4, which say nothing about the kernels
+    alloc_ms = []
+    for _ in range(min(steps, 9)):
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        run_alloc()
+        eb.record()
+        eb.synchronize()
+        alloc_ms.append(ea.elapsed_time(eb))
     ms, ms_min = time_calls(ctx, run, steps, warmup)
     # size-independent check at full size: the result's column sums are the source's row sums, entry count kept
     T = keep[0]
@@ -416,10 +438,14 @@ def section_transpose(ctx, args, peak, steps, warmup):
     scale = float(b.abs().max().item()) or 1.0
     drift = float((a - b).abs().max().item()) / scale
     ab = D.algorithmic_bytes("transpose")
-    entry = roofline_entry("transpose", "C3", "transpose_bitrank_kernel", ab, ms, peak, D.nnz,
+    entry = roofline_entry("transpose", cfg, TRANSPOSE_KERNELS.get(cfg, "transpose"), ab, ms, peak, D.nnz,
                            {"ms_min": ms_min, "first_call_ms": first_ms, "nnz": D.nnz,
-                            "what": "sb200_transpose_dev: allocation of the result from the pool + (cached) band plan + placement kernel + "
-                                    "the result's tile plans; first_call_ms includes building the band plan",
+                            "allocating_form_ms": {"median": float(np.median(alloc_ms)), "min": float(np.min(alloc_ms)),
+                                                   "max": float(np.max(alloc_ms)), "calls": len(alloc_ms)},
+                            "what": "sb200_transpose_into: (cached) plan + placement kernel(s) into the result of an earlier "
+                                    "sb200_transpose_dev; allocating_form_ms = sb200_transpose_dev itself (result and, on the two-split "
+                                    "path's first call, the 16 B/entry record stream from the pool + the result's tile plans); "
+                                    "first_call_ms includes building the plan",
                             "check": {"shape_and_nnz_ok": bool(ok), "colSums(T) vs rowSums(A) max rel diff": drift}})
     info = {"workload": spec.name, "nnz": D.nnz, "generate_s": gen_s, "steps": steps}
     keep.clear()
@@ -780,6 +806,11 @@ def run_b200(args, ops):
             by_op["transpose@C3"], sections["transpose"] = section_transpose(ctx, args, peak, big_steps, args.warmup)
         except Exception as e:
             sections["transpose"] = {"error": f"{type(e).__name__}: {e}"}
+        for cfg in ("C2", "C4"):  # the tall configs: two stable stream splits (transpose_split.cu)
+            try:
+                by_op[f"transpose@{cfg}"], sections[f"transpose_{cfg}"] = section_transpose(ctx, args, peak, max(3, big_steps // 2), args.warmup, cfg)
+            except Exception as e:
+                sections[f"transpose_{cfg}"] = {"error": f"{type(e).__name__}: {e}"}
     c4_strong = None
     if not args.no_products:
         try:

@@ -111,6 +111,11 @@ int sb200_spmv_dev(sb200_matrix* m, const double* d_v /* ncol */, double* d_y /*
 int sb200_spmv_t_dev(sb200_matrix* m, const double* d_v /* nrow */, double* d_y /* ncol */);
 /* Result stays in HBM as a new handle that owns its arrays (Dim swapped). */
 int sb200_transpose_dev(sb200_matrix* m, sb200_matrix** out);
+/* The same transpose (RcppSparse.h:375-385) written into a result that sb200_transpose_dev produced earlier for a matrix
+ * of this structure (t: Dim swapped, same nnz, owns its arrays): nothing is allocated, t's tile plans stay (they depend on
+ * the structure only), its cached layouts are dropped.  For mirrors whose values change and whose transpose is wanted
+ * again (sb200_matrix_refresh_values + this).  Blocking. */
+int sb200_transpose_into(sb200_matrix* m, sb200_matrix* t);
 /* d[k] /= divisor for k < n, on the handle's stream (mean scaling after a cross-rank reduce). */
 int sb200_vec_div_dev(sb200_matrix* m, double* d, int64_t n, double divisor);
 

@@ -20,7 +20,7 @@ SYMBOLS = [
     "sb200_matrix_adopt_device", "sb200_matrix_destroy", "sb200_matrix_dims", "sb200_matrix_refresh_values",
     "sb200_matrix_set_stream", "sb200_matrix_sync", "sb200_matrix_device_arrays", "sb200_col_sums",
     "sb200_row_sums", "sb200_col_means", "sb200_row_means", "sb200_spmv", "sb200_spmv_t", "sb200_transpose",
-    "sb200_col_sums_dev", "sb200_row_sums_dev", "sb200_spmv_dev", "sb200_spmv_t_dev", "sb200_transpose_dev",
+    "sb200_col_sums_dev", "sb200_row_sums_dev", "sb200_spmv_dev", "sb200_spmv_t_dev", "sb200_transpose_dev", "sb200_transpose_into",
     "sb200_vec_div_dev", "sb200_launch_count", "sb200_algorithmic_bytes", "sb200_synth_create",
     "sb200_synth_vector_dev", "sb200_matrix_download_columns", "sb200_matrix_row_path", "sb200_matrix_row_companion",
     "sb200_crossprod", "sb200_crossprod_dev", "sb200_matrix_band_companion", "sb200_matrix_layouts", "sb200_matrix_layout_bytes", "sb200_trim",
@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
         "sb200_spmv_dev": ([vp, vp, vp], C.c_int),
         "sb200_spmv_t_dev": ([vp, vp, vp], C.c_int),
         "sb200_transpose_dev": ([vp, pp], C.c_int),
+        "sb200_transpose_into": ([vp, vp], C.c_int),
         "sb200_vec_div_dev": ([vp, vp, i64, dbl], C.c_int),
         "sb200_launch_count": ([], i64),
         "sb200_algorithmic_bytes": ([vp, C.c_char_p, C.POINTER(i64)], C.c_int),

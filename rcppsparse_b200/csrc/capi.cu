@@ -511,6 +511,20 @@ int sb200_transpose_dev(sb200_matrix* m, sb200_matrix** out) {
   return SB200_OK;
 }
 
+int sb200_transpose_into(sb200_matrix* m, sb200_matrix* t) {
+  ENTER(m);
+  SB_TRY(check_handle(t));
+  if (t == m || !t->owns_arrays || t->device != m->device || t->nrow != m->ncol || t->ncol != m->nrow || t->nnz != m->nnz)
+    return fail(SB200_E_INVALID, "transpose_into: the target is not a transpose of this shape that owns its arrays");
+  // t's own work first (its stream may differ from m's), then the kernels on m's stream write its arrays
+  if (t->stream != m->stream && cudaStreamSynchronize(t->stream) != cudaSuccess) return fail(SB200_E_CUDA, "transpose_into: stream sync failed");
+  drop_row_companion(t);
+  drop_band_companion(t, t->stream);
+  int rc = transpose_device(m, t->d_p, t->d_i, t->d_x);
+  if (cudaStreamSynchronize(m->stream) != cudaSuccess && rc == SB200_OK) rc = fail(SB200_E_CUDA, "transpose_into: stream sync failed");
+  return rc;
+}
+
 // ---- host-buffer form: stage through the handle's device buffers ---------------------------------------------
 static int run_to_host(sb200_matrix* m, SweepMode mode, const double* v_host, int64_t v_len, double divisor,
                        double* out_host, int64_t out_len) {

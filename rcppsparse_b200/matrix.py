@@ -262,6 +262,10 @@ class DeviceMatrix:
         check(_lib.lib().sb200_transpose_dev(self._h, C.byref(out)))
         return DeviceMatrix(out.value)
 
+    def transpose_into(self, t: "DeviceMatrix") -> None:
+        """The transpose again, into a result of `transpose_dev` of this structure: no allocation (sparse_b200.h)."""
+        check(_lib.lib().sb200_transpose_into(self._h, t._h))
+
     def synth_vector_dev(self, seed: int, begin: int, n: int, d_out) -> None:
         check(_lib.lib().sb200_synth_vector_dev(self._h, seed, begin, n, _ptr(d_out)))
 

@@ -254,6 +254,32 @@ def test_transpose_fuzz_every_path(monkeypatch):
     assert r.returncode == 0 and "bit-exact" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("path", ["place", "split", "banded"])
+def test_transpose_into_an_existing_result(path, monkeypatch, checker):
+    """sb200_transpose_into: the transpose again into a result of the same structure (new values), nothing allocated; the
+    target's cached layouts go, its tile plans stay valid (sums on it are checked); wrong shapes are refused."""
+    monkeypatch.setenv("SB200_TRANSPOSE_PATH", path)
+    spec = synth.powerlaw_spec(20_000, 3_000, 40.0, 55, row_levels=3)
+    i, p, x = synth.generate_host(spec)
+    x2 = np.random.default_rng(3).standard_normal(len(x))
+    with DeviceMatrix.from_host(i, p, x, spec.nrow, spec.ncol) as D, D.transpose_dev() as T:
+        T.row_companion(1)
+        D.refresh_values(x2)
+        n0 = _lib.lib().sb200_launch_count()
+        D.transpose_into(T)
+        assert _lib.lib().sb200_launch_count() - n0 <= 2 and not (T.layouts() & 1)
+        ti, tp, tx = T.download_columns()
+        wi, wp, wx = checker.transpose(i, p, x2, spec.nrow, spec.ncol)
+        assert np.array_equal(tp, wp) and np.array_equal(ti, wi) and np.array_equal(bits(tx), bits(wx))
+        args = (wi, wp, wx, spec.ncol, spec.nrow)
+        oracle.assert_within("colSums", T.col_sums(), checker.colSums(*args), *args, tol=TOL)
+        oracle.assert_within("rowSums", T.row_sums(), checker.rowSums(*args), *args, tol=TOL)
+        with pytest.raises(SparseB200Error):
+            D.transpose_into(D)
+        with DeviceMatrix.from_host(i[:p[5]], p[:6], x[:p[5]], spec.nrow, 5) as other, pytest.raises(SparseB200Error):
+            other.transpose_into(T)
+
+
 def test_transpose_golden_edges_on_both_paths(golden, monkeypatch):
     g = golden
     for path in ("place", "banded", "split"):
