@@ -58,9 +58,6 @@ struct SplitPlan {
   int32_t* d_segfirst = nullptr; // [nb+1] first segment of every band
   uint32_t* d_segcur = nullptr;  // [nseg << sh] where every row's cursor starts in a segment (filled on the first call)
   bool segcur_ready = false;
-  void* d_rec = nullptr;         // the 16 B/entry record stream, kept from the second call on (a handle that transposes again
-  size_t rec_bytes = 0;          // and again should not go through the pool for 16N bytes every time); else per-call scratch
-  int calls = 0;
   unsigned int* d_counters = nullptr;  // [2] tickets of the two passes
   size_t bytes = 0;
 };
@@ -658,12 +655,11 @@ void free_split_plan(SplitPlan* sp, cudaStream_t s) {
   pool_free(sp->d_seg, s);
   pool_free(sp->d_segfirst, s);
   pool_free(sp->d_segcur, s);
-  pool_free(sp->d_rec, s);
   pool_free(sp->d_counters, s);
   delete sp;
 }
 
-int64_t split_plan_bytes(const SplitPlan* sp) { return sp ? static_cast<int64_t>(sp->bytes + (sp->d_rec ? sp->rec_bytes : 0)) : 0; }
+int64_t split_plan_bytes(const SplitPlan* sp) { return sp ? static_cast<int64_t>(sp->bytes) : 0; }
 
 // Whether the two-split path can take this matrix: key tables within shared memory, the (tile, band) table and the
 // record stream within what the device has left.
@@ -682,7 +678,7 @@ bool split_transpose_fits(const sb200_matrix* m) {
   const int64_t ntiles = (m->nnz + te_ - 1) / te_;
   const size_t table = sizeof(int32_t) * static_cast<size_t>(nb) * static_cast<size_t>(ntiles);
   const size_t stream = sizeof(Rec) * static_cast<size_t>(m->nnz);
-  const size_t need = (m->plan_split ? 0 : 3 * table) + ((m->plan_split && m->plan_split->d_rec) ? 0 : stream) + (64ull << 20);
+  const size_t need = (m->plan_split ? 0 : 3 * table) + stream + (64ull << 20);
   return device_free_bytes() > need + need / 8;
 }
 
@@ -789,10 +785,9 @@ int transpose_split_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, 
   const SplitPlan* sp = m->plan_split;
   tr.mark();
   SB_CUDA(cudaMemcpyAsync(d_p_out, sp->d_rowptr, sizeof(int32_t) * (static_cast<size_t>(m->nrow) + 1), cudaMemcpyDeviceToDevice, st));
-  Rec* rec = static_cast<Rec*>(m->plan_split->d_rec);
+  Rec* rec = nullptr;  // per-call scratch: the pool hands the same block back call after call (measured: no jitter from it)
   const size_t n = static_cast<size_t>(m->nnz);
-  int rc = SB200_OK;
-  if (!rec) rc = pool_alloc(reinterpret_cast<void**>(&rec), padded_bytes(sizeof(Rec) * n), st);
+  int rc = pool_alloc(reinterpret_cast<void**>(&rec), padded_bytes(sizeof(Rec) * n), st);
   if (rc == SB200_OK) {
     SplitArgs a;
     memset(&a, 0, sizeof(a));
@@ -839,12 +834,7 @@ int transpose_split_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, 
     tr.mark();
     if (e != cudaSuccess) rc = cuda_fail(e, "transpose: stream split launch", __FILE__, __LINE__);
   }
-  if (rc == SB200_OK && ++m->plan_split->calls >= 2 && (m->plan_split->d_rec || device_free_bytes() > 4 * padded_bytes(sizeof(Rec) * n))) {
-    m->plan_split->d_rec = rec;  // second transpose of this handle: keep the stream for the next one
-    m->plan_split->rec_bytes = padded_bytes(sizeof(Rec) * n);
-  } else if (rec != m->plan_split->d_rec) {
-    pool_free(rec, st);
-  }
+  pool_free(rec, st);
   tr.report(sp, cached);
   return rc;
 }
