@@ -136,7 +136,7 @@ def test_crossprod_known_answer_on_the_vignette_matrix():
 
 @pytest.mark.parametrize("n_super,chunk", [(1, 1000), (8, 1000), (5, 37), (13, 100000)])
 def test_two_level_transpose_spec_is_the_canonical_transpose(n_super, chunk):
-    """tools/transpose_two_level_spec.py (the plan for tall matrices): a stable partition into
+    """tools/transpose_two_level_spec.py (the specification of transpose_split.cu): a stable partition into
     row super-bands followed by a stable split inside each is the counting-sort transpose, bit for bit."""
     import importlib.util
 
@@ -147,6 +147,7 @@ def test_two_level_transpose_spec_is_the_canonical_transpose(n_super, chunk):
     spec_.loader.exec_module(mod)
     for spec in (synth.powerlaw_spec(3000, 400, 25.0, 5, row_levels=4), synth.uniform_spec(20000, 150, 0.004, 6)):
         i, p, x = synth.generate_host(spec)
-        ti, tp, tx = mod.transpose_two_level(i, p, x, spec.nrow, spec.ncol, n_super, chunk)
         ri, rp, rx = oracle.Port().transpose(i, p, x, spec.nrow, spec.ncol)
-        assert np.array_equal(tp, rp) and np.array_equal(ti, ri) and np.array_equal(tx.view(np.uint64), rx.view(np.uint64))
+        for shift in (None, 6):  # equal row counts per band, or the device's bands (row >> shift) with its 4096-entry chunks
+            ti, tp, tx = mod.transpose_two_level(i, p, x, spec.nrow, spec.ncol, n_super, 4096 if shift else chunk, shift)
+            assert np.array_equal(tp, rp) and np.array_equal(ti, ri) and np.array_equal(tx.view(np.uint64), rx.view(np.uint64))
