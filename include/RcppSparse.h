@@ -8,7 +8,7 @@
 //   rows cols nrow ncol n_nonzero nonzeros innerIndexPtr outerIndexPtr InnerNNZs   :44-51, :357-359
 //   colSums rowSums colMeans rowMeans                      reference :131-156  -> sb200_col_sums ... sb200_row_means
 //   crossprod                                              reference :158-194  -> sb200_crossprod
-//   transpose (and the vignette's t)                       reference :375-385  -> sb200_transpose
+//   transpose (and the vignette's t)                       reference :375-385  -> sb200_transpose / sb200_sharded_transpose
 //   wrap, clone, at, operator(), operator[]                reference :387-394, :54-73 (host side, unchanged semantics)
 //   InnerIterator                                          reference :218-233 (host side, unchanged)
 //   Rcpp::traits::Exporter<RcppSparse::Matrix>             reference :398-423
@@ -284,8 +284,8 @@ public:
     Rcpp::NumericVector tx(nnz);
     tdim[0] = Dim[1];
     tdim[1] = Dim[0];
-    Lease l(*this, false);
-    b200::check(sb200_transpose(l.m, tp.begin(), ti.begin(), tx.begin()));
+    Lease l(*this, true);
+    b200::check(l.s ? sb200_sharded_transpose(l.s, tp.begin(), ti.begin(), tx.begin()) : sb200_transpose(l.m, tp.begin(), ti.begin(), tx.begin()));
     return Matrix(tx, ti, tp, tdim);
   }
   Matrix t() { return transpose(); }
@@ -454,7 +454,7 @@ private:
   std::shared_ptr<b200::Mirror> mirror_;
 
   // The device handle(s) for one call: uploaded from the slots as they are now, dropped again at the end of the call
-  // unless the Matrix is resident.  multi = the op has a several-GPU form (the sweeps; not transpose / crossprod).
+  // unless the Matrix is resident.  multi = the op has a several-GPU form (the sweeps and the transpose; not crossprod).
   struct Lease {
     b200::Mirror& mm;
     sb200_matrix* m = nullptr;

@@ -231,6 +231,10 @@ int sb200_sharded_col_means(sb200_sharded* s, double* out /* ncol */);
 int sb200_sharded_row_means(sb200_sharded* s, double* out /* nrow */);
 int sb200_sharded_spmv(sb200_sharded* s, const double* v /* ncol */, double* y /* nrow */);
 int sb200_sharded_spmv_t(sb200_sharded* s, const double* v /* nrow */, double* y /* ncol */);
+/* Matrix::transpose() (RcppSparse.h:375-385) of the whole matrix into host arrays: local transposes on every device, row
+ * pieces exchanged over peer memory in block (= column) order, every device copies its rows home.
+ * Bit-exact like the one-GPU transpose.  Blocking. */
+int sb200_sharded_transpose(sb200_sharded* s, int32_t* p_out /* nrow + 1 */, int32_t* i_out /* nnz */, double* x_out /* nnz */);
 
 /* Scratch, results and cached layouts come from the device's stream-ordered memory pool, which keeps freed blocks
  * for reuse (a multi-GB cudaMalloc/cudaFree pair costs as much as a sweep).  sb200_trim synchronises the device and

@@ -26,7 +26,7 @@ SYMBOLS = [
     "sb200_crossprod", "sb200_crossprod_dev", "sb200_matrix_band_companion", "sb200_matrix_layouts", "sb200_matrix_layout_bytes", "sb200_trim",
     "sb200_col_sums_in_rows", "sb200_gather_block",
     "sb200_sharded_create", "sb200_sharded_destroy", "sb200_sharded_info", "sb200_sharded_block", "sb200_sharded_col_sums",
-    "sb200_sharded_row_sums", "sb200_sharded_col_means", "sb200_sharded_row_means", "sb200_sharded_spmv", "sb200_sharded_spmv_t",
+    "sb200_sharded_row_sums", "sb200_sharded_col_means", "sb200_sharded_row_means", "sb200_sharded_spmv", "sb200_sharded_spmv_t", "sb200_sharded_transpose",
     "sb200_exchange_create", "sb200_exchange_connect", "sb200_exchange_destroy", "sb200_exchange_window",
     "sb200_exchange_gather", "sb200_exchange_reduce", "sb200_exchange_push_rows", "sb200_exchange_barrier", "sb200_exchange_status",
 ]
@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
         "sb200_sharded_row_means": ([vp, vp], C.c_int),
         "sb200_sharded_spmv": ([vp, vp, vp], C.c_int),
         "sb200_sharded_spmv_t": ([vp, vp, vp], C.c_int),
+        "sb200_sharded_transpose": ([vp, vp, vp, vp], C.c_int),
         "sb200_crossprod": ([vp, vp], C.c_int),
         "sb200_crossprod_dev": ([vp, vp], C.c_int),
         "sb200_exchange_create": ([C.c_int, i64, pp, vp], C.c_int),

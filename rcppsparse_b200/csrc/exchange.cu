@@ -20,10 +20,11 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "pushrows.cuh"
 
 namespace sb200 {
 
-constexpr int XG_MAX_RANKS = 16;
+constexpr int XG_MAX_RANKS = PUSH_MAX_RANKS;
 constexpr size_t XG_HEADER_BYTES = 4096;  // epoch slots, error word, CTA counter, gate word (see XG_W_*); data starts at 4096
 constexpr uint32_t XG_MAGIC = 0x5B2000E8u;
 
@@ -133,84 +134,21 @@ __global__ void __launch_bounds__(256) xg_push_kernel(XgPeers peers, int rank, i
 // segment).  dst_off[r] = where my segment of row r starts in the owner's output (entries); owner of r = the q with
 // rb[q] <= r < rb[q+1]; column ids leave as GLOBAL ids (local id + col_offset).  The barrier at the end = all landed.
 struct XgPushRows {
-  const int32_t* p_loc;    // [nrow + 1] my local transpose: row pointer,
-  const int32_t* cols;     // column ids (local),
-  const double* vals;      // values
-  const int64_t* dst_off;  // [nrow]
-  int32_t nrow;
-  int32_t col_offset;
-  int32_t rb[XG_MAX_RANKS + 1];
+  PushRowsSrc src;
   size_t cols_off[XG_MAX_RANKS];  // byte offset of the int32 output region inside peer q's window
   size_t vals_off[XG_MAX_RANKS];  // byte offset of the double output region
 };
 
+struct XgWindowDest {
+  const XgPeers& peers;
+  const XgPushRows& a;
+  __device__ __forceinline__ int32_t* cols(int q) const { return reinterpret_cast<int32_t*>(peers.base[q] + a.cols_off[q]); }
+  __device__ __forceinline__ double* vals(int q) const { return reinterpret_cast<double*>(peers.base[q] + a.vals_off[q]); }
+};
+
 __global__ void __launch_bounds__(256) xg_push_rows_kernel(XgPeers peers, int rank, int world, XgPushRows a, uint32_t epoch,
                                                             unsigned long long timeout_ns) {
-  constexpr int U = 4;
-  const int lane = threadIdx.x & 31;
-  const int64_t n_groups = (static_cast<int64_t>(a.nrow) + 31) / 32;
-  const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n_groups; w += warps) {
-    const int64_t r = w * 32 + lane;
-    int32_t s = 0, len = 0;
-    int q = 0;
-    int64_t d0 = 0;
-    if (r < a.nrow) {
-      s = a.p_loc[r];
-      len = a.p_loc[r + 1] - s;
-      d0 = a.dst_off[r];
-      while (q + 1 < world && a.rb[q + 1] <= r) ++q;
-    }
-    int32_t incl = len;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int32_t up = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += up;
-    }
-    const int32_t excl = incl - len;
-    const int32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-    const uint32_t d0_lo = static_cast<uint32_t>(d0), d0_hi = static_cast<uint32_t>(static_cast<uint64_t>(d0) >> 32);
-    for (int32_t base = 0; base < tot; base += 32 * U) {
-      int32_t cc[U];
-      double xx[U];
-      int32_t* cdst[U];
-      double* xdst[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int32_t t = base + u * 32 + lane;
-        int l = 0;  // largest l with excl[l] <= t (skips empty segments)
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-          const int cand = l + step;
-          const int32_t e = __shfl_sync(0xffffffffu, excl, cand & 31);
-          if (cand < 32 && e <= t) l = cand;
-        }
-        const int32_t rs = __shfl_sync(0xffffffffu, s, l);
-        const int32_t re = __shfl_sync(0xffffffffu, excl, l);
-        const int ql = __shfl_sync(0xffffffffu, q, l);
-        const int64_t dl = static_cast<int64_t>((static_cast<uint64_t>(__shfl_sync(0xffffffffu, d0_hi, l)) << 32) |
-                                                 __shfl_sync(0xffffffffu, d0_lo, l));
-        cdst[u] = nullptr;
-        xdst[u] = nullptr;
-        cc[u] = 0;
-        xx[u] = 0.0;
-        if (t < tot) {
-          const int32_t j = t - re;
-          cc[u] = a.cols[rs + j] + a.col_offset;
-          xx[u] = a.vals[rs + j];
-          cdst[u] = reinterpret_cast<int32_t*>(peers.base[ql] + a.cols_off[ql]) + dl + j;
-          xdst[u] = reinterpret_cast<double*>(peers.base[ql] + a.vals_off[ql]) + dl + j;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (cdst[u]) {
-          *cdst[u] = cc[u];
-          *xdst[u] = xx[u];
-        }
-      }
-    }
-  }
+  push_rows_body(a.src, world, XgWindowDest{peers, a});
   xg_tail_barrier(peers, rank, world, epoch, timeout_ns);
 }
 
@@ -570,13 +508,13 @@ int sb200_exchange_push_rows(sb200_exchange* x, void* cuda_stream, const int32_t
   if (nrow < 0 || !row_bounds || !cols_offsets || !vals_offsets || (nrow > 0 && (!d_p_loc || !d_dst_off)))
     return fail(SB200_E_INVALID, "sb200_exchange_push_rows: bad argument");
   XgPushRows a;
-  a.p_loc = d_p_loc;
-  a.cols = d_cols;
-  a.vals = d_vals;
-  a.dst_off = d_dst_off;
-  a.nrow = nrow;
-  a.col_offset = col_offset;
-  for (int q = 0; q <= x->world; ++q) a.rb[q] = row_bounds[q];
+  a.src.p_loc = d_p_loc;
+  a.src.cols = d_cols;
+  a.src.vals = d_vals;
+  a.src.dst_off = d_dst_off;
+  a.src.nrow = nrow;
+  a.src.col_offset = col_offset;
+  for (int q = 0; q <= x->world; ++q) a.src.rb[q] = row_bounds[q];
   for (int q = 0; q < x->world; ++q) {
     if (cols_offsets[q] < static_cast<int64_t>(XG_HEADER_BYTES) || vals_offsets[q] < static_cast<int64_t>(XG_HEADER_BYTES) ||
         (cols_offsets[q] & 3) || (vals_offsets[q] & 7))

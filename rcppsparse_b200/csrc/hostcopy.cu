@@ -34,7 +34,11 @@ struct Pool {
   Worker w[MAX_WORKERS];
 };
 
-Pool g_pool;
+// One set of staging buffers and streams per device: the single-process sharding layer copies to and from several
+// devices at once (one worker thread per device, each over its own PCIe link); a single shared set was torn down and
+// rebuilt — 16 cudaHostAlloc calls — every time the device changed, and serialised the devices behind one mutex.
+constexpr int MAX_DEVICES = 16;
+Pool g_pools[MAX_DEVICES];
 
 int worker_count() {
   static const int n = [] {
@@ -50,7 +54,7 @@ int worker_count() {
 }
 
 // call with g_pool.mu held
-cudaError_t ensure_pool(int device) {
+cudaError_t ensure_pool(Pool& g_pool, int device) {
   if (g_pool.device == device && g_pool.n == worker_count()) return cudaSuccess;
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return e;
@@ -69,7 +73,7 @@ cudaError_t ensure_pool(int device) {
   for (int k = 0; k < n; ++k) {
     Worker& w = g_pool.w[k];
     for (int b = 0; b < 2; ++b) {
-      e = cudaHostAlloc(reinterpret_cast<void**>(&w.buf[b]), CHUNK, cudaHostAllocDefault);
+      e = cudaHostAlloc(reinterpret_cast<void**>(&w.buf[b]), CHUNK, cudaHostAllocPortable);
       if (e != cudaSuccess) return e;
       e = cudaEventCreateWithFlags(&w.ev[b], cudaEventDisableTiming);
       if (e != cudaSuccess) return e;
@@ -127,8 +131,10 @@ void run_d2h(int device, Worker& w, int k, int n, unsigned char* dst, const unsi
 
 int staged(int device, void* a, const void* b, size_t bytes, bool up) {
   if (bytes == 0) return SB200_OK;
+  if (device < 0 || device >= MAX_DEVICES) return fail(SB200_E_INVALID, "staged copy: device index out of range");
+  Pool& g_pool = g_pools[device];
   std::lock_guard<std::mutex> lock(g_pool.mu);
-  cudaError_t e = ensure_pool(device);
+  cudaError_t e = ensure_pool(g_pool, device);
   if (e != cudaSuccess) return cuda_fail(e, "pinned staging buffers", __FILE__, __LINE__);
   const int n = g_pool.n;
   cudaError_t errs[MAX_WORKERS];

@@ -15,14 +15,19 @@
 // All launches come from the calling thread, device after device, nothing blocks until the final synchronisation.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <chrono>
 #include <new>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "common.cuh"
+#include "pushrows.cuh"
 
 struct sb200_sharded {
   uint32_t magic;
@@ -117,6 +122,52 @@ int run_rows(sb200_sharded* s, SweepMode mode, const double* v_host, double divi
     if (e != cudaSuccess && rc == SB200_OK) rc = cuda_fail(e, "sharded row sweep", __FILE__, __LINE__);
   }
   return rc;
+}
+
+
+// ---- sharded transpose: local transposes, row segments pushed to the devices that own the rows -------
+struct TpPtrs {
+  const int32_t* p[PUSH_MAX_RANKS];  // row pointers of the devices' local transposes (peer-readable)
+};
+struct PtrDest {
+  int32_t* c[PUSH_MAX_RANKS];
+  double* v[PUSH_MAX_RANKS];
+  __device__ __forceinline__ int32_t* cols(int q) const { return c[q]; }
+  __device__ __forceinline__ double* vals(int q) const { return v[q]; }
+};
+
+// cnt[r] = entries of row r over all column blocks
+__global__ void shard_row_counts_kernel(const TpPtrs tp, int world, int32_t nrow, uint32_t* __restrict__ cnt) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < nrow; r += stride) {
+    uint32_t n = 0;
+    for (int k = 0; k < world; ++k) n += static_cast<uint32_t>(tp.p[k][r + 1] - tp.p[k][r]);
+    cnt[r] = n;
+  }
+}
+
+struct RowBounds {
+  int32_t rb[PUSH_MAX_RANKS + 1];
+};
+
+// dst[k * nrow + r] = where block k's piece of row r starts inside the arrays of the row's owner: the row's place in
+// the result (P[r], relative to the owner's first row) plus the pieces of the blocks before k — block order = column order
+__global__ void shard_row_dst_kernel(const TpPtrs tp, int world, int32_t nrow, const int32_t* __restrict__ P, const RowBounds b,
+                                     int64_t* __restrict__ dst) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < nrow; r += stride) {
+    int q = 0;
+    while (q + 1 < world && b.rb[q + 1] <= r) ++q;
+    int64_t run = static_cast<int64_t>(P[r]) - P[b.rb[q]];
+    for (int k = 0; k < world; ++k) {
+      dst[static_cast<int64_t>(k) * nrow + r] = run;
+      run += tp.p[k][r + 1] - tp.p[k][r];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) push_rows_local_kernel(const PushRowsSrc a, int world, const PtrDest d) {
+  push_rows_body(a, world, d);
 }
 
 }  // namespace
@@ -287,6 +338,199 @@ int sb200_sharded_spmv(sb200_sharded* s, const double* v, double* y) {
   SB_TRY(check_sharded(s));
   if (s->ncol > 0 && !v) return fail(SB200_E_INVALID, "operand vector is NULL");
   return run_rows(s, SWEEP_SPMV, v, 0.0, y);
+}
+
+
+// CSC(A^T) of the whole matrix into host arrays (RcppSparse.h:375-385): every device transposes its column block, the
+// row counts are summed and scanned on device 0 (p_out), rows are dealt to the devices in nnz-balanced contiguous
+// ranges, every device pushes its piece of every row straight to its place in the owner's arrays over peer memory
+// (block order = column order inside a row: bit-exact), and every owner copies its range of i_out / x_out to the host
+// over its own PCIe link.
+int sb200_sharded_transpose(sb200_sharded* s, int32_t* p_out, int32_t* i_out, double* x_out) {
+  SB_TRY(check_sharded(s));
+  if (!p_out || (s->nnz > 0 && (!i_out || !x_out))) return fail(SB200_E_INVALID, "NULL output array");
+  const int W = s->world;
+  const int32_t nrow = s->nrow;
+  if (s->nnz == 0 || nrow == 0) {
+    for (int64_t r = 0; r <= nrow; ++r) p_out[r] = 0;
+    return SB200_OK;
+  }
+  DeviceGuard restore(s->blocks[0]->device);
+  const bool trace = getenv("SB200_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[sb200 trace] sharded transpose: %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
+  // 1. local transposes, concurrently (the entry point blocks)
+  std::vector<sb200_matrix*> T(W, nullptr);
+  std::vector<int> rcs(W, SB200_OK);
+  std::vector<std::string> errs(W);
+  {
+    std::vector<std::thread> workers;
+    for (int k = 0; k < W; ++k)
+      workers.emplace_back([&, k] {
+        rcs[k] = sb200_transpose_dev(s->blocks[k], &T[k]);
+        if (rcs[k] != SB200_OK) errs[k] = sb200_last_error();
+      });
+    for (auto& w : workers) w.join();
+  }
+  struct Scratch {  // everything below is released on every way out
+    std::vector<sb200_matrix*>& T;
+    sb200_sharded* s;
+    uint32_t* cnt = nullptr;
+    int32_t* P = nullptr;
+    void* ws = nullptr;
+    int64_t* dst = nullptr;
+    int32_t* tpc = nullptr;          // device 0: copies of every block's row pointer
+    std::vector<int64_t*> dstk;      // device k: its slice of dst
+    std::vector<int32_t*> oc;        // the owners' arrays: plain cudaMalloc, visible to the peers (pool memory is not)
+    std::vector<double*> ov;
+    ~Scratch() {
+      for (int k = 0; k < s->world; ++k) {
+        DeviceGuard g(s->blocks[k]->device);
+        cudaStreamSynchronize(s->blocks[k]->stream);
+        if (k < static_cast<int>(oc.size()) && oc[k]) cudaFree(oc[k]);
+        if (k < static_cast<int>(ov.size()) && ov[k]) cudaFree(ov[k]);
+        if (k > 0 && k < static_cast<int>(dstk.size())) pool_free(dstk[k], s->blocks[k]->stream);
+        if (k == 0) {
+          pool_free(tpc, s->blocks[0]->stream);
+          pool_free(cnt, s->blocks[0]->stream);
+          pool_free(P, s->blocks[0]->stream);
+          pool_free(ws, s->blocks[0]->stream);
+          pool_free(dst, s->blocks[0]->stream);
+        }
+        if (T[k]) sb200_matrix_destroy(T[k]);
+      }
+      cudaGetLastError();
+    }
+  } sc{T, s};
+  lap("local transposes");
+  for (int k = 0; k < W; ++k)
+    if (rcs[k] != SB200_OK) return fail(rcs[k], "sharded transpose, column block " + std::to_string(k) + ": " + errs[k]);
+  // 2. row counts over the blocks -> p_out (device 0)
+  sb200_matrix* m0 = s->blocks[0];
+  cudaStream_t st0 = m0->stream;
+  TpPtrs tp;
+  const size_t ws_bytes = scan_workspace_bytes(nrow);
+  {
+    DeviceGuard g(m0->device);
+    // the library's arrays are pool memory, which peers cannot address: bring the (small) row pointers to device 0
+    const size_t pb = sizeof(int32_t) * (static_cast<size_t>(nrow) + 1);
+    SB_TRY(pool_alloc(reinterpret_cast<void**>(&sc.tpc), pb * W, st0));
+    for (int k = 0; k < PUSH_MAX_RANKS; ++k) tp.p[k] = k < W ? sc.tpc + static_cast<size_t>(k) * (nrow + 1) : nullptr;
+    for (int k = 0; k < W; ++k)
+      SB_CUDA(cudaMemcpyPeerAsync(sc.tpc + static_cast<size_t>(k) * (nrow + 1), m0->device, T[k]->d_p, s->blocks[k]->device, pb, st0));
+    SB_TRY(pool_alloc(reinterpret_cast<void**>(&sc.cnt), sizeof(uint32_t) * static_cast<size_t>(nrow), st0));
+    SB_TRY(pool_alloc(reinterpret_cast<void**>(&sc.P), sizeof(int32_t) * (static_cast<size_t>(nrow) + 1), st0));
+    SB_TRY(pool_alloc(&sc.ws, ws_bytes, st0));
+    SB_TRY(pool_alloc(reinterpret_cast<void**>(&sc.dst), sizeof(int64_t) * static_cast<size_t>(W) * nrow, st0));
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>((static_cast<int64_t>(nrow) + 255) / 256, 4096));
+    shard_row_counts_kernel<<<grid, 256, 0, st0>>>(tp, W, nrow, sc.cnt);
+    count_launch();
+    SB_CUDA(cudaGetLastError());
+    SB_TRY(exclusive_scan_u32(st0, sc.cnt, sc.P, nrow, nullptr, sc.ws, ws_bytes));
+    SB_CUDA(cudaMemcpyAsync(p_out, sc.P, sizeof(int32_t) * (static_cast<size_t>(nrow) + 1), cudaMemcpyDeviceToHost, st0));
+    SB_CUDA(cudaStreamSynchronize(st0));
+    lap("row counts, scan, p_out");
+    if (p_out[nrow] != s->nnz) return fail(SB200_E_CUDA, "sharded transpose: the blocks' row counts do not add up to nnz");
+    // 3. rows dealt to the devices: nnz-balanced contiguous ranges
+    RowBounds rb;
+    rb.rb[0] = 0;
+    for (int q = 1; q < W; ++q) {
+      const int64_t target = (s->nnz * q) / W;
+      int32_t lo = rb.rb[q - 1], hi = nrow;
+      while (lo < hi) {
+        const int32_t mid = lo + ((hi - lo) >> 1);
+        if (p_out[mid] < target)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      rb.rb[q] = lo;
+    }
+    for (int q = W; q <= PUSH_MAX_RANKS; ++q) rb.rb[q] = nrow;
+    shard_row_dst_kernel<<<grid, 256, 0, st0>>>(tp, W, nrow, sc.P, rb, sc.dst);
+    count_launch();
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(st0));
+    // every device gets its slice of dst
+    sc.dstk.assign(W, nullptr);
+    sc.dstk[0] = sc.dst;
+    for (int k = 1; k < W; ++k) {
+      DeviceGuard gk(s->blocks[k]->device);
+      SB_TRY(pool_alloc(reinterpret_cast<void**>(&sc.dstk[k]), sizeof(int64_t) * static_cast<size_t>(nrow), s->blocks[k]->stream));
+      SB_CUDA(cudaMemcpyPeerAsync(sc.dstk[k], s->blocks[k]->device, sc.dst + static_cast<int64_t>(k) * nrow, m0->device,
+                                  sizeof(int64_t) * static_cast<size_t>(nrow), s->blocks[k]->stream));
+    }
+    // 4. the owners' arrays
+    sc.oc.assign(W, nullptr);
+    sc.ov.assign(W, nullptr);
+    for (int q = 0; q < W; ++q) {
+      DeviceGuard gq(s->blocks[q]->device);
+      const size_t n = static_cast<size_t>(p_out[rb.rb[q + 1]] - p_out[rb.rb[q]]);
+      SB_CUDA(cudaMalloc(reinterpret_cast<void**>(&sc.oc[q]), padded_bytes(sizeof(int32_t) * (n + 1))));
+      SB_CUDA(cudaMalloc(reinterpret_cast<void**>(&sc.ov[q]), padded_bytes(sizeof(double) * (n + 1))));
+    }
+    // 5. every device pushes its pieces
+    PtrDest pd;
+    for (int q = 0; q < PUSH_MAX_RANKS; ++q) {
+      pd.c[q] = q < W ? sc.oc[q] : nullptr;
+      pd.v[q] = q < W ? sc.ov[q] : nullptr;
+    }
+    for (int k = 0; k < W; ++k) {
+      DeviceGuard gk(s->blocks[k]->device);
+      PushRowsSrc a;
+      a.p_loc = T[k]->d_p;
+      a.cols = T[k]->d_i;
+      a.vals = T[k]->d_x;
+      a.dst_off = sc.dstk[k];
+      a.nrow = nrow;
+      a.col_offset = static_cast<int32_t>(s->bounds[k]);
+      for (int q = 0; q <= PUSH_MAX_RANKS; ++q) a.rb[q] = rb.rb[q];
+      int64_t blocks = ((static_cast<int64_t>(nrow) + 31) / 32 + 7) / 8;
+      if (blocks > 592) blocks = 592;
+      push_rows_local_kernel<<<static_cast<unsigned>(blocks), 256, 0, s->blocks[k]->stream>>>(a, W, pd);
+      count_launch();
+      SB_CUDA(cudaGetLastError());
+    }
+    for (int k = 0; k < W; ++k) {
+      DeviceGuard gk(s->blocks[k]->device);
+      SB_CUDA(cudaStreamSynchronize(s->blocks[k]->stream));
+    }
+    lap("push");
+    // 6. every owner brings its range home over its own link
+    std::vector<int> drc(W, SB200_OK);
+    std::vector<std::thread> workers;
+    for (int q = 0; q < W; ++q)
+      workers.emplace_back([&, q] {
+        const int64_t o = p_out[rb.rb[q]];
+        const size_t n = static_cast<size_t>(p_out[rb.rb[q + 1]] - o);
+        if (n == 0) return;
+        const int dev = s->blocks[q]->device;
+        if (cudaSetDevice(dev) != cudaSuccess) {
+          drc[q] = SB200_E_CUDA;
+          return;
+        }
+        const size_t bi = sizeof(int32_t) * n, bx = sizeof(double) * n;
+        if (bi >= STAGED_COPY_MIN_BYTES && host_is_pageable(i_out + o))
+          drc[q] = staged_d2h(dev, i_out + o, sc.oc[q], bi);
+        else if (cudaMemcpy(i_out + o, sc.oc[q], bi, cudaMemcpyDeviceToHost) != cudaSuccess)
+          drc[q] = SB200_E_CUDA;
+        if (drc[q] != SB200_OK) return;
+        if (bx >= STAGED_COPY_MIN_BYTES && host_is_pageable(x_out + o))
+          drc[q] = staged_d2h(dev, x_out + o, sc.ov[q], bx);
+        else if (cudaMemcpy(x_out + o, sc.ov[q], bx, cudaMemcpyDeviceToHost) != cudaSuccess)
+          drc[q] = SB200_E_CUDA;
+      });
+    for (auto& w : workers) w.join();
+    lap("copies to the host");
+    for (int q = 0; q < W; ++q)
+      if (drc[q] != SB200_OK) return fail(drc[q], "sharded transpose: copying rows of device " + std::to_string(q) + " to the host failed");
+  }
+  return SB200_OK;
 }
 
 }  // extern "C"

@@ -350,6 +350,15 @@ class ShardedHostMatrix:
             raise ValueError("A^T v: v must have nrow entries")
         return self._vec(_lib.lib().sb200_sharded_spmv_t, self.ncol, _ptr(v))
 
+    def transpose_host(self):
+        """CSC(A^T) of the whole matrix: local transposes on every GPU, row pieces exchanged over peer memory, every
+        GPU copies its rows home (sparse_b200.h sb200_sharded_transpose; reference RcppSparse.h:375-385)."""
+        p = np.empty(self.nrow + 1, np.int32)
+        i = np.empty(self.nnz, np.int32)
+        x = np.empty(self.nnz, np.float64)
+        check(_lib.lib().sb200_sharded_transpose(self._h, _ptr(p), _ptr(i), _ptr(x)))
+        return i, p, x
+
 
 class Matrix:
     """Python mirror of ``RcppSparse::Matrix`` (reference RcppSparse.h:25-395), hot-path members.
@@ -540,7 +549,7 @@ class Matrix:
 
     # ---- RcppSparse.h:375-385 ---------------------------------------------------------------------------------------------
     def transpose(self) -> "Matrix":
-        ti, tp, tx = self._call(False, lambda m: m.transpose_host())
+        ti, tp, tx = self._call(True, lambda m: m.transpose_host())
         return Matrix(tx, ti, tp, np.array([self.cols(), self.rows()], np.int32), self._device, self._pin)
 
     t = transpose  # the vignette lists .t() (Documentation.Rmd:250); the header defines transpose()

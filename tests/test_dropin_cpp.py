@@ -122,6 +122,12 @@ def test_dropin_header_on_two_gpus(shim, monkeypatch):
     y = np.empty(spec.nrow)
     assert shim.dropin_spmv(0, i, p, x, spec.nrow, spec.ncol, x.shape[0], v, y) == 0, shim.dropin_last_error()
     oracle.assert_within("spmv", y, chk.spmv(*args, v), *args, v=v)
+    # Matrix::transpose() on two GPUs (sb200_sharded_transpose): bit for bit
+    tp, ti, tx, td = np.empty(spec.nrow + 1, np.int32), np.empty(x.shape[0], np.int32), np.empty(x.shape[0]), np.empty(2, np.int32)
+    assert shim.dropin_transpose(i, p, x, spec.nrow, spec.ncol, x.shape[0], tp, ti, tx, td) == 0, shim.dropin_last_error()
+    wi, wp, wx = chk.transpose(*args)
+    assert td.tolist() == [spec.ncol, spec.nrow] and np.array_equal(tp, wp) and np.array_equal(ti, wi)
+    assert np.array_equal(tx.view(np.uint64), wx.view(np.uint64))
 
 
 @pytest.mark.gpu

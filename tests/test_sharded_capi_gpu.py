@@ -47,6 +47,31 @@ def test_sharded_handle_matches_the_reference(case, n_gpus):
         assert np.array_equal(r1.view(np.uint64), r2.view(np.uint64)), "rank-ordered reduction of deterministic partials"
 
 
+@pytest.mark.parametrize("n_gpus", [1, 2, 4, 8])
+@pytest.mark.parametrize("case", sorted(CASES) + ["C2_5pct"])
+def test_sharded_transpose_bit_exact(case, n_gpus):
+    """sb200_sharded_transpose: local transposes, row pieces pushed over peer memory in block (= column) order, every
+    device copies its rows home — the canonical CSC of A^T bit for bit, twice (cached plans the second time)."""
+    if n_gpus > _lib.device_count():
+        pytest.skip(f"needs {n_gpus} GPUs")
+    spec = synth.config("C2", 0.05) if case == "C2_5pct" else CASES[case]()
+    i, p, x = synth.generate_host(spec)
+    wi, wp, wx = oracle.best().transpose(i, p, x, spec.nrow, spec.ncol)
+    with ShardedHostMatrix(i, p, x, spec.nrow, spec.ncol, n_gpus) as S:
+        for _ in range(2):
+            ti, tp, tx = S.transpose_host()
+            assert np.array_equal(tp, wp) and np.array_equal(ti, wi) and np.array_equal(tx.view(np.uint64), wx.view(np.uint64))
+
+
+def test_sharded_transpose_golden_edges(golden):
+    g = golden
+    for n_gpus in gpu_counts()[:2]:
+        with ShardedHostMatrix(g["i"], g["p"], g["x"], g["nrow"], g["ncol"], n_gpus) as S:
+            ti, tp, tx = S.transpose_host()
+        assert np.array_equal(tp, g["t_p"]) and np.array_equal(ti, g["t_i"]) and np.array_equal(
+            np.asarray(tx).view(np.uint64), np.asarray(g["t_x"], np.float64).view(np.uint64))
+
+
 def test_sharded_handle_golden_edges(golden):
     g = golden
     a = (g["i"], g["p"], g["x"], g["nrow"], g["ncol"])
