@@ -34,34 +34,6 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 size_t padded_bytes(size_t bytes) { return ((bytes + 15) / 16) * 16 + 16; }
 
-// Stream-ordered allocation from the device's default memory pool, with the pool told to keep
-// freed memory (release threshold = max): after the first use of a size class an allocation is
-// a pool lookup, not a driver call — a multi-GB cudaMalloc/cudaFree pair costs milliseconds,
-// comparable to the sweeps themselves.
-int pool_alloc(void** out, size_t bytes, cudaStream_t s) {
-  static std::atomic<unsigned> configured{0};
-  int dev = 0;
-  SB_CUDA(cudaGetDevice(&dev));
-  if (dev < 32 && !(configured.load() & (1u << dev))) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    cudaGetLastError();
-    configured.fetch_or(1u << dev);
-  }
-  cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, s);
-  if (e != cudaSuccess) {
-    *out = nullptr;
-    return cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
-  }
-  return SB200_OK;
-}
-void pool_free(void* ptr, cudaStream_t s) {
-  if (ptr) cudaFreeAsync(ptr, s);
-}
-
 static int require_device(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -181,6 +153,7 @@ size_t device_free_bytes() {
     if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
       free_b += static_cast<size_t>(reserved - used);
+    free_b += pool_idle_bytes(dev);  // blocks the library's own cache holds: handed back to the driver when it runs short
   }
   cudaGetLastError();
   return free_b;
@@ -273,6 +246,8 @@ int sb200_trim(int device) {
   SB_TRY(require_device(device));
   DeviceGuard guard(device);
   if (!guard.ok) return fail(SB200_E_CUDA, "cudaSetDevice failed");
+  SB_CUDA(cudaDeviceSynchronize());
+  pool_release_idle(device);
   SB_CUDA(cudaDeviceSynchronize());
   cudaMemPool_t pool;
   SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -579,9 +554,18 @@ int sb200_spmv_t(sb200_matrix* m, const double* v, double* y) {
 int sb200_transpose(sb200_matrix* m, int32_t* p_out, int32_t* i_out, double* x_out) {
   ENTER(m);
   if (!p_out || (m->nnz > 0 && (!i_out || !x_out))) return fail(SB200_E_INVALID, "NULL output array");
+  const bool trace = getenv("SB200_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto phase = [&](const char* what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[sb200 trace] transpose to host: %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   sb200_matrix* t = nullptr;
   SB_TRY(alloc_matrix(m->device, m->ncol, m->nrow, m->nnz, &t));
   cudaStreamSynchronize(t->stream);  // t's arrays were allocated in its own stream's order, written in m's
+  phase("result allocated");
   int rc = transpose_device(m, t->d_p, t->d_i, t->d_x);
   cudaError_t e = cudaSuccess;
   if (rc == SB200_OK) {
@@ -593,14 +577,18 @@ int sb200_transpose(sb200_matrix* m, int32_t* p_out, int32_t* i_out, double* x_o
     if (e == cudaSuccess && m->nnz > 0 && !stage_i) e = cudaMemcpyAsync(i_out, t->d_i, bi, cudaMemcpyDeviceToHost, m->stream);
     if (e == cudaSuccess && m->nnz > 0 && !stage_x) e = cudaMemcpyAsync(x_out, t->d_x, bx, cudaMemcpyDeviceToHost, m->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);  // the transposed arrays are complete
+    phase("transposed on the device (plan + kernels, p' copied)");
     if (e == cudaSuccess && stage_i) rc = staged_d2h(m->device, i_out, t->d_i, bi);
+    phase("i' to the host");
     if (e == cudaSuccess && rc == SB200_OK && stage_x) rc = staged_d2h(m->device, x_out, t->d_x, bx);
+    phase("x' to the host");
   }
   if (rc != SB200_OK || e != cudaSuccess) {
     cudaStreamSynchronize(m->stream);  // nothing on m's stream still touches t's arrays when they are freed
     cudaGetLastError();
   }
   free_matrix(t);
+  phase("result freed");
   if (rc != SB200_OK) return rc;
   if (e != cudaSuccess) return cuda_fail(e, "download of the transposed matrix", __FILE__, __LINE__);
   return SB200_OK;

@@ -179,6 +179,8 @@ int finish_matrix(sb200_matrix* m, unsigned flags);  // validate + plan + worksp
 size_t padded_bytes(size_t bytes);
 int pool_alloc(void** out, size_t bytes, cudaStream_t s);  // stream-ordered, from a retaining pool
 void pool_free(void* ptr, cudaStream_t s);
+size_t pool_idle_bytes(int device);     // freed blocks the library's cache holds on that device (blockcache.cu)
+void pool_release_idle(int device);     // hand them back to the driver pool; the device is current and synchronised
 size_t device_free_bytes();  // driver-free plus what the pool holds unused
 
 }  // namespace sb200

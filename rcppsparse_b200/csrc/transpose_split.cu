@@ -36,6 +36,7 @@
 
 #include <algorithm>
 #include <new>
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -714,6 +715,14 @@ static int build_split_plan(sb200_matrix* m, SplitPlan** out) {
       }
     }
   } guard{&sp, st, drop};
+  const bool trace = getenv("SB200_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto phase = [&](const char* what) {  // host wall clock: a stall inside a driver call shows here, not in the device's event times
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[sb200 trace] split plan: %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   const size_t ws_bytes = scan_workspace_bytes(cells > m->nrow ? cells : m->nrow);
   SB_TRY(pool_alloc(reinterpret_cast<void**>(&d_hc), sizeof(uint32_t) * static_cast<size_t>(cells), st));
   SB_TRY(pool_alloc(reinterpret_cast<void**>(&d_rowcnt), sizeof(uint32_t) * static_cast<size_t>(m->nrow), st));
@@ -726,6 +735,7 @@ static int build_split_plan(sb200_matrix* m, SplitPlan** out) {
   SB_TRY(pool_alloc(reinterpret_cast<void**>(&sp->d_counters), sizeof(unsigned int) * 2, st));
   sp->bytes = sizeof(int32_t) * (static_cast<size_t>(m->nrow) + 1 + static_cast<size_t>(cells) + nb + 1 + static_cast<size_t>(nt) + 1) + 8;
 
+  phase("tables allocated");
   SB_CUDA(cudaMemsetAsync(d_rowcnt, 0, sizeof(uint32_t) * static_cast<size_t>(m->nrow), st));
   int64_t grid = nt < static_cast<int64_t>(m->sm_count) * 4 ? nt : static_cast<int64_t>(m->sm_count) * 4;
   split_hist_kernel<<<static_cast<unsigned>(grid), SP_THREADS, sizeof(uint32_t) * nb, st>>>(m->d_i, m->nnz, sp->sh, nb, sp->te, nt, d_hc, d_rowcnt);
@@ -744,8 +754,10 @@ static int build_split_plan(sb200_matrix* m, SplitPlan** out) {
   SB_CUDA(cudaGetLastError());
   // pass-2 units: every band's stream in segments of SP_SEG_CHUNKS chunks
   std::vector<int32_t> bs(static_cast<size_t>(nb) + 1), seg, segfirst(static_cast<size_t>(nb) + 1);
+  phase("kernels enqueued");
   SB_CUDA(cudaMemcpyAsync(bs.data(), sp->d_bstart, sizeof(int32_t) * (nb + 1), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
+  phase("band starts on the host");
   const int seg_chunks = segment_chunks();
   sp->seg_chunks = seg_chunks;
   const int64_t seglen = static_cast<int64_t>(seg_chunks) * sp->te;
@@ -766,6 +778,7 @@ static int build_split_plan(sb200_matrix* m, SplitPlan** out) {
   SB_CUDA(cudaMemcpyAsync(sp->d_seg, seg.data(), sizeof(int32_t) * seg.size(), cudaMemcpyHostToDevice, st));
   SB_CUDA(cudaMemcpyAsync(sp->d_segfirst, segfirst.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
   SB_CUDA(cudaStreamSynchronize(st));
+  phase("segments uploaded");
   guard.armed = false;
   *out = sp;
   return SB200_OK;
