@@ -18,8 +18,21 @@
 namespace sb200 {
 namespace {
 
-constexpr size_t CHUNK = 8u << 20;
 constexpr int MAX_WORKERS = 16;
+
+// bytes per pinned chunk (SB200_COPY_CHUNK_KB; fixed for the life of the process).  One-shot C2 transpose on B200, 12 workers:
+// 512 KB 100 ms, 1 MB 78, 2 MB 62-64, 4 MB 64-66, 8 MB 68-72 (small chunks pay an event wait each, large ones fall out of
+// the host's cache between the CPU copy and the DMA).
+size_t chunk_bytes() {
+  static const size_t n = [] {
+    long kb = 2048;
+    if (const char* e = getenv("SB200_COPY_CHUNK_KB")) kb = atol(e);
+    if (kb < 64) kb = 64;
+    if (kb > 65536) kb = 65536;
+    return static_cast<size_t>(kb) << 10;
+  }();
+  return n;
+}
 
 struct Worker {
   unsigned char* buf[2] = {nullptr, nullptr};
@@ -46,7 +59,7 @@ int worker_count() {
     if (const char* e = getenv("SB200_COPY_THREADS")) v = atoi(e);
     if (v <= 0) {
       const unsigned hc = std::thread::hardware_concurrency();
-      v = hc >= 16 ? 8 : (hc >= 8 ? 4 : 2);
+      v = hc >= 16 ? 12 : (hc >= 8 ? 4 : 2);  // 16-core B200 host, one-shot C2 transpose: 4 threads 92-113 ms, 8 75-85, 12 70-73, 16 68-71
     }
     return v > MAX_WORKERS ? MAX_WORKERS : v;
   }();
@@ -73,7 +86,7 @@ cudaError_t ensure_pool(Pool& g_pool, int device) {
   for (int k = 0; k < n; ++k) {
     Worker& w = g_pool.w[k];
     for (int b = 0; b < 2; ++b) {
-      e = cudaHostAlloc(reinterpret_cast<void**>(&w.buf[b]), CHUNK, cudaHostAllocPortable);
+      e = cudaHostAlloc(reinterpret_cast<void**>(&w.buf[b]), chunk_bytes(), cudaHostAllocPortable);
       if (e != cudaSuccess) return e;
       e = cudaEventCreateWithFlags(&w.ev[b], cudaEventDisableTiming);
       if (e != cudaSuccess) return e;
@@ -88,6 +101,7 @@ cudaError_t ensure_pool(Pool& g_pool, int device) {
 
 void run_h2d(int device, Worker& w, int k, int n, unsigned char* dst, const unsigned char* src, size_t bytes, cudaError_t* err) {
   cudaError_t e = cudaSetDevice(device);
+  const size_t CHUNK = chunk_bytes();
   const size_t chunks = (bytes + CHUNK - 1) / CHUNK;
   int it = 0;
   for (size_t c = k; c < chunks && e == cudaSuccess; c += n, ++it) {
@@ -105,6 +119,7 @@ void run_h2d(int device, Worker& w, int k, int n, unsigned char* dst, const unsi
 
 void run_d2h(int device, Worker& w, int k, int n, unsigned char* dst, const unsigned char* src, size_t bytes, cudaError_t* err) {
   cudaError_t e = cudaSetDevice(device);
+  const size_t CHUNK = chunk_bytes();
   const size_t chunks = (bytes + CHUNK - 1) / CHUNK;
   // software pipeline: the DMA of my next chunk runs while I memcpy the previous one out of pinned memory
   size_t prev_off = 0, prev_len = 0;

@@ -51,12 +51,28 @@ int check_sharded(const sb200_sharded* s) {
   return SB200_OK;
 }
 
+struct WallTrace {  // SB200_TRACE=1: host wall clock of the phases of an entry point on stderr
+  bool on = getenv("SB200_TRACE") != nullptr;
+  const char* title;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  explicit WallTrace(const char* what) : title(what) {}
+  void phase(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[sb200 trace] %s: %s %.2f ms\n", title, what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
 void destroy_sharded(sb200_sharded* s) {
   if (!s) return;
+  WallTrace tr("sharded destroy");
   for (sb200_matrix* m : s->blocks)
     if (m) sb200_matrix_destroy(m);
+  tr.phase("blocks");
   for (sb200_exchange* x : s->windows)
     if (x) sb200_exchange_destroy(x);
+  tr.phase("windows");
   s->magic = 0;
   delete s;
 }
@@ -224,6 +240,7 @@ int sb200_sharded_create(const int32_t* i, const int32_t* p, const double* x, in
   s->blocks.assign(n_gpus, nullptr);
   s->windows.assign(n_gpus, nullptr);
   // upload the blocks concurrently: one worker per device
+  WallTrace tr("sharded create");
   std::vector<int> rcs(n_gpus, SB200_OK);
   std::vector<std::string> errs(n_gpus);
   std::vector<std::thread> workers;
@@ -248,6 +265,7 @@ int sb200_sharded_create(const int32_t* i, const int32_t* p, const double* x, in
     });
   }
   for (auto& w : workers) w.join();
+  tr.phase("blocks uploaded");
   for (int k = 0; k < n_gpus; ++k)
     if (rcs[k] != SB200_OK) {
       const int rc = rcs[k];
@@ -264,8 +282,10 @@ int sb200_sharded_create(const int32_t* i, const int32_t* p, const double* x, in
     unsigned char handle[64];
     rc = sb200_exchange_create(s->devices[k], 2 * vec, &s->windows[k], handle);
   }
+  tr.phase("windows allocated");
   if (rc == SB200_OK) rc = exchange_connect_local(s->windows.data(), n_gpus);
   cudaSetDevice(prev);
+  tr.phase("peers connected");
   if (rc != SB200_OK) {
     const std::string msg = sb200_last_error();
     destroy_sharded(s);
