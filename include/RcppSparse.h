@@ -474,8 +474,10 @@ private:
         s = mm.sharded;
       } else {
         if (!mm.handle)
+          // a per-call mirror (dropped by ~Lease while the slots are still protected) leaves `i` on the host until an op
+          // reads it: colSums / colMeans never do (reference :133-135), so they upload 8 of the 12 bytes per entry
           b200::check(sb200_matrix_create(A.i.begin(), A.p.begin(), A.x.begin(), A.Dim[0], A.Dim[1], A.x.size(),
-                                          b200::device_from_env(), 0u, &mm.handle));
+                                          b200::device_from_env(), mm.resident ? 0u : SB200_LAZY_ROWS, &mm.handle));
         m = mm.handle;
       }
       mm.src_x = A.x.begin();

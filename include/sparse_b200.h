@@ -42,6 +42,12 @@ extern "C" {
                                 * for pageable memory (pinned-chunk worker threads): 123-170 ms vs 30 ms for 1.2 GB */
 #define SB200_NO_VALIDATE 2u /* skip the structure-validation kernel (trusted producer, benchmarks) */
 #define SB200_NO_ROW_PLAN 4u /* sb200_matrix_create: do not prepare the row-band plan during the upload (column sweeps only) */
+#define SB200_LAZY_ROWS 8u   /* sb200_matrix_create: leave the row indices `i` on the host until an op reads them.  columnSums /
+                                * colSums / colMeans never read `i` (reference src/example.cpp:28-30, RcppSparse.h:133-135), so a
+                                * one-shot call uploads 8 of the 12 bytes per entry; `i` is uploaded (and, unless SB200_NO_VALIDATE,
+                                * checked) by the first entry point that needs it.  The caller keeps `i` alive and unchanged until
+                                * then or until destroy (true for the drop-in header's per-call mirror: R protects the slots for
+                                * the lifetime of the Matrix).  Ignored by sb200_sharded_create. */
 
 /* Opaque device-resident mirror of one dgCMatrix (or of one column block of it, which is
  * itself a valid dgCMatrix with the same nrow — the unit of multi-GPU sharding).

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(PKG, "libsparse_b200.so")
 
 OK = 0
 E_INVALID, E_CUDA, E_NOMEM, E_STRUCTURE, E_NODEVICE, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
-PIN_HOST, NO_VALIDATE, NO_ROW_PLAN = 1, 2, 4
+PIN_HOST, NO_VALIDATE, NO_ROW_PLAN, LAZY_ROWS = 1, 2, 4, 8
 
 # every symbol include/sparse_b200.h declares (tests/test_boundary.py checks header == this list == .so)
 SYMBOLS = [

@@ -48,20 +48,27 @@ struct DeviceCache {
   bool configured = false;
 };
 
-std::mutex g_mu;
-std::unordered_map<void*, Block> g_live;  // blocks in use, by address
-DeviceCache g_dev[MAX_DEVICES];
-uint64_t g_tick = 0;
-
+// The cache lives for the whole process and is never destroyed: handles may be torn down by a host language's
+// finalisers after static destructors have started.
+struct Cache {
+  std::mutex mu;
+  std::unordered_map<void*, Block> live;  // blocks in use, by address
+  DeviceCache dev[MAX_DEVICES];
+  uint64_t tick = 0;
+};
+Cache& cache() {
+  static Cache* c = new Cache();
+  return *c;
+}
 size_t capacity_class(size_t bytes) {
   if (bytes < 16) bytes = 16;
   const size_t step = bytes >= LARGE_FROM ? LARGE_STEP : SMALL_STEP;
   return (bytes + step - 1) / step * step;
 }
 
-// g_mu held
+// cache().mu held
 void configure(int dev) {
-  DeviceCache& dc = g_dev[dev];
+  DeviceCache& dc = cache().dev[dev];
   if (dc.configured) return;
   dc.configured = true;
   cudaMemPool_t pool;
@@ -75,7 +82,7 @@ void configure(int dev) {
   cudaGetLastError();
 }
 
-// g_mu held; the block leaves the cache for the driver pool, ordered after its last use
+// cache().mu held; the block leaves the cache for the driver pool, ordered after its last use
 void release_to_driver(Block& b, cudaStream_t s) {
   if (b.ev) {
     cudaStreamWaitEvent(s, b.ev, 0);
@@ -85,9 +92,9 @@ void release_to_driver(Block& b, cudaStream_t s) {
   cudaGetLastError();
 }
 
-// g_mu held
+// cache().mu held
 void flush_device(int dev, cudaStream_t s) {
-  DeviceCache& dc = g_dev[dev];
+  DeviceCache& dc = cache().dev[dev];
   for (auto& kv : dc.idle) release_to_driver(kv.second, s);
   dc.idle.clear();
   dc.idle_bytes = 0;
@@ -107,39 +114,48 @@ int pool_alloc(void** out, size_t bytes, cudaStream_t s) {
   }
   if (dev < 0 || dev >= MAX_DEVICES) return fail(SB200_E_INVALID, "device index out of range");
   const size_t cap = capacity_class(bytes);
-  std::lock_guard<std::mutex> lock(g_mu);
-  configure(dev);
-  DeviceCache& dc = g_dev[dev];
-  auto it = dc.idle.lower_bound(cap);
-  if (it != dc.idle.end() && it->first <= cap + cap / 8 + (cap >= LARGE_FROM ? LARGE_STEP : SMALL_STEP)) {
-    Block b = it->second;
-    dc.idle.erase(it);
-    dc.idle_bytes -= b.cap;
-    cudaError_t e = cudaStreamWaitEvent(s, b.ev, 0);
-    if (e != cudaSuccess) {  // keep the block out of circulation rather than hand it out unordered
-      release_to_driver(b, static_cast<cudaStream_t>(0));
-      return cuda_fail(e, "cudaStreamWaitEvent (block cache)", __FILE__, __LINE__);
+  size_t idle_now = 0;
+  {
+    std::lock_guard<std::mutex> lock(cache().mu);
+    configure(dev);
+    DeviceCache& dc = cache().dev[dev];
+    auto it = dc.idle.lower_bound(cap);
+    if (it != dc.idle.end() && it->first <= cap + cap / 8 + (cap >= LARGE_FROM ? LARGE_STEP : SMALL_STEP)) {
+      Block b = it->second;
+      dc.idle.erase(it);
+      dc.idle_bytes -= b.cap;
+      cudaError_t e = cudaStreamWaitEvent(s, b.ev, 0);
+      if (e != cudaSuccess) {  // keep the block out of circulation rather than hand it out unordered
+        release_to_driver(b, static_cast<cudaStream_t>(0));
+        return cuda_fail(e, "cudaStreamWaitEvent (block cache)", __FILE__, __LINE__);
+      }
+      cache().live[b.ptr] = b;
+      *out = b.ptr;
+      return SB200_OK;
     }
-    g_live[b.ptr] = b;
-    *out = b.ptr;
-    return SB200_OK;
+    idle_now = dc.idle_bytes;
   }
+  // miss: the driver pool serves it (outside the lock: growing the pool can take milliseconds, and the workers of the
+  // one-process sharding layer allocate on several devices at once)
   Block b;
   b.cap = cap;
   b.device = dev;
   const auto t0 = std::chrono::steady_clock::now();
   cudaError_t e = cudaMallocAsync(&b.ptr, cap, s);
-  if (e == cudaErrorMemoryAllocation && dc.idle_bytes > 0) {  // idle blocks of other sizes are in the way
+  if (e == cudaErrorMemoryAllocation && idle_now > 0) {  // idle blocks of other sizes are in the way
     cudaGetLastError();
     DeviceGuard guard(dev);
     cudaDeviceSynchronize();
-    flush_device(dev, static_cast<cudaStream_t>(0));
+    {
+      std::lock_guard<std::mutex> lock(cache().mu);
+      flush_device(dev, static_cast<cudaStream_t>(0));
+    }
     cudaDeviceSynchronize();
     e = cudaMallocAsync(&b.ptr, cap, s);
   }
   if (trace) {  // a request the driver pool was slow to serve shows up as milliseconds here
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (ms > 0.5) fprintf(stderr, "[sb200 trace] cudaMallocAsync of %.1f MB took %.2f ms (cache idle %.1f MB)\n", cap / 1048576.0, ms, dc.idle_bytes / 1048576.0);
+    if (ms > 0.5) fprintf(stderr, "[sb200 trace] cudaMallocAsync of %.1f MB took %.2f ms (cache idle %.1f MB)\n", cap / 1048576.0, ms, idle_now / 1048576.0);
   }
   if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
   e = cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming);
@@ -147,23 +163,26 @@ int pool_alloc(void** out, size_t bytes, cudaStream_t s) {
     cudaFreeAsync(b.ptr, s);
     return cuda_fail(e, "cudaEventCreate (block cache)", __FILE__, __LINE__);
   }
-  g_live[b.ptr] = b;
+  {
+    std::lock_guard<std::mutex> lock(cache().mu);
+    cache().live[b.ptr] = b;
+  }
   *out = b.ptr;
   return SB200_OK;
 }
 
 void pool_free(void* ptr, cudaStream_t s) {
   if (!ptr) return;
-  std::lock_guard<std::mutex> lock(g_mu);
-  auto it = g_live.find(ptr);
-  if (it == g_live.end()) {  // not ours (never happens inside the library): plain stream-ordered free
+  std::lock_guard<std::mutex> lock(cache().mu);
+  auto it = cache().live.find(ptr);
+  if (it == cache().live.end()) {  // not ours (never happens inside the library): plain stream-ordered free
     cudaFreeAsync(ptr, s);
     cudaGetLastError();
     return;
   }
   Block b = it->second;
-  g_live.erase(it);
-  DeviceCache& dc = g_dev[b.device];
+  cache().live.erase(it);
+  DeviceCache& dc = cache().dev[b.device];
   if (cudaEventRecord(b.ev, s) != cudaSuccess || b.cap > dc.limit) {
     cudaGetLastError();
     cudaEventDestroy(b.ev);
@@ -171,7 +190,7 @@ void pool_free(void* ptr, cudaStream_t s) {
     release_to_driver(b, s);
     return;
   }
-  b.tick = ++g_tick;
+  b.tick = ++cache().tick;
   dc.idle.emplace(b.cap, b);
   dc.idle_bytes += b.cap;
   while (dc.idle_bytes > dc.limit && !dc.idle.empty()) {  // oldest first
@@ -186,14 +205,14 @@ void pool_free(void* ptr, cudaStream_t s) {
 
 size_t pool_idle_bytes(int device) {
   if (device < 0 || device >= MAX_DEVICES) return 0;
-  std::lock_guard<std::mutex> lock(g_mu);
-  return g_dev[device].idle_bytes;
+  std::lock_guard<std::mutex> lock(cache().mu);
+  return cache().dev[device].idle_bytes;
 }
 
 // the device must be current and idle (sb200_trim synchronises it first)
 void pool_release_idle(int device) {
   if (device < 0 || device >= MAX_DEVICES) return;
-  std::lock_guard<std::mutex> lock(g_mu);
+  std::lock_guard<std::mutex> lock(cache().mu);
   flush_device(device, static_cast<cudaStream_t>(0));
 }
 

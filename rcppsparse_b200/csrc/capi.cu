@@ -133,7 +133,7 @@ static int enqueue_finish(sb200_matrix* m, unsigned flags) {
   if (m->stage_len < 1) m->stage_len = 1;
   SB_TRY(pool_alloc(reinterpret_cast<void**>(&m->d_stage_in), padded_bytes(sizeof(double) * static_cast<size_t>(m->stage_len)), m->stream));
   SB_TRY(pool_alloc(reinterpret_cast<void**>(&m->d_stage_out), padded_bytes(sizeof(double) * static_cast<size_t>(m->stage_len)), m->stream));
-  if (!(flags & SB200_NO_VALIDATE)) SB_TRY(validate_structure(m));
+  if (!(flags & SB200_NO_VALIDATE)) SB_TRY(validate_structure(m, m->lazy_i == nullptr));
   SB_TRY(build_sweep_plan(m));
   return SB200_OK;
 }
@@ -215,14 +215,39 @@ int finish_matrix(sb200_matrix* m, unsigned flags) {
   return SB200_OK;
 }
 
+// SB200_LAZY_ROWS: the row indices are still in the caller's array.  Bring them over (and check them, unless the mirror
+// was created with SB200_NO_VALIDATE) before the first op that reads d_i.  A failed check leaves the mirror as it was:
+// the next row-indexed call tries again and fails the same way; the column sweeps keep working, like the reference's
+// colSums on a matrix whose `i` is garbage (it never reads it, RcppSparse.h:133-135).
+int ensure_rows(sb200_matrix* m) {
+  if (!m->lazy_i) return SB200_OK;
+  const int32_t* i = m->lazy_i;
+  const size_t bi = sizeof(int32_t) * static_cast<size_t>(m->nnz);
+  if (m->nnz > 0 && bi >= STAGED_COPY_MIN_BYTES && host_is_pageable(i)) {
+    SB_CUDA(cudaStreamSynchronize(m->stream));  // d_i was allocated in this stream's order; the workers use their own
+    SB_TRY(staged_h2d(m->device, m->d_i, i, bi));
+  } else if (m->nnz > 0) {
+    SB_CUDA(cudaMemcpyAsync(m->d_i, i, bi, cudaMemcpyHostToDevice, m->stream));
+    SB_CUDA(cudaStreamSynchronize(m->stream));  // the caller's array is not needed after this call
+  }
+  if (m->lazy_validate) SB_TRY(validate_rows(m));
+  m->lazy_i = nullptr;
+  return SB200_OK;
+}
+
 }  // namespace sb200
 
 using namespace sb200;
 
-#define ENTER(m)                        \
+// ENTER_COLS: entry points that never read the row indices (column sweeps, bookkeeping).  ENTER: everything else — a
+// mirror created with SB200_LAZY_ROWS gets its `i` now.
+#define ENTER_COLS(m)                   \
   SB_TRY(check_handle(m));              \
   DeviceGuard guard_((m)->device);      \
   if (!guard_.ok) return fail(SB200_E_CUDA, "cudaSetDevice failed")
+#define ENTER(m)  \
+  ENTER_COLS(m);  \
+  SB_TRY(ensure_rows(m))
 
 extern "C" {
 
@@ -267,13 +292,16 @@ int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int
   if (!guard.ok) return fail(SB200_E_CUDA, "cudaSetDevice failed");
   sb200_matrix* m = nullptr;
   SB_TRY(alloc_matrix(device, nrow, ncol, nnz, &m));
+  const bool lazy = (flags & SB200_LAZY_ROWS) && nnz > 0;  // `i` stays with the caller until an op reads it
+  m->lazy_i = lazy ? i : nullptr;
+  m->lazy_validate = !(flags & SB200_NO_VALIDATE);
   const size_t bi = sizeof(int32_t) * static_cast<size_t>(nnz), bp = sizeof(int32_t) * (static_cast<size_t>(ncol) + 1),
                bx = sizeof(double) * static_cast<size_t>(nnz);
   bool pinned_i = false, pinned_x = false;
   if ((flags & SB200_PIN_HOST) && nnz > 0) {
     // R owns these pages; pinning the enclosing pages lets the copy engine stream them directly
-    pinned_i = cudaHostRegister(const_cast<int32_t*>(i), bi, cudaHostRegisterReadOnly) == cudaSuccess;
-    if (!pinned_i) pinned_i = cudaHostRegister(const_cast<int32_t*>(i), bi, cudaHostRegisterDefault) == cudaSuccess;
+    if (!lazy) pinned_i = cudaHostRegister(const_cast<int32_t*>(i), bi, cudaHostRegisterReadOnly) == cudaSuccess;
+    if (!lazy && !pinned_i) pinned_i = cudaHostRegister(const_cast<int32_t*>(i), bi, cudaHostRegisterDefault) == cudaSuccess;
     pinned_x = cudaHostRegister(const_cast<double*>(x), bx, cudaHostRegisterReadOnly) == cudaSuccess;
     if (!pinned_x) pinned_x = cudaHostRegister(const_cast<double*>(x), bx, cudaHostRegisterDefault) == cudaSuccess;
     cudaGetLastError();
@@ -286,7 +314,7 @@ int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int
   std::string x_err_text;  // sb200_last_error() is per thread: the values-upload thread reports through this
   // Pageable arrays (what R owns) go through the worker threads of hostcopy.cu; pinned or registered ones are
   // handed to the copy engine directly.
-  const bool stage_i = nnz > 0 && !pinned_i && bi >= STAGED_COPY_MIN_BYTES && host_is_pageable(i);
+  const bool stage_i = nnz > 0 && !lazy && !pinned_i && bi >= STAGED_COPY_MIN_BYTES && host_is_pageable(i);
   const bool stage_x = nnz > 0 && !pinned_x && bx >= STAGED_COPY_MIN_BYTES && host_is_pageable(x);
   cudaStream_t xs = nullptr;
   cudaError_t e = cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking);
@@ -303,7 +331,7 @@ int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int
     if (allocated) cudaEventDestroy(allocated);
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_p, p, bp, cudaMemcpyHostToDevice, m->stream);
-  if (e == cudaSuccess && nnz > 0) {
+  if (e == cudaSuccess && nnz > 0 && !lazy) {
     if (stage_i)
       rc = staged_h2d(device, m->d_i, i, bi);
     else
@@ -320,7 +348,7 @@ int sb200_matrix_create(const int32_t* i, const int32_t* p, const double* x, int
     }
   }
   if (e == cudaSuccess && rc == SB200_OK) rc = enqueue_finish(m, flags);
-  if (e == cudaSuccess && rc == SB200_OK && nnz > 0 && m->nrow > 0 && !(flags & SB200_NO_ROW_PLAN)) {
+  if (e == cudaSuccess && rc == SB200_OK && nnz > 0 && m->nrow > 0 && !lazy && !(flags & SB200_NO_ROW_PLAN)) {
     // plan failures here are not fatal: the row sweeps retry (or fall back to the L2 path) on first use
     const std::string keep = t_last_error;
     if (decide_row_path(m) == SB200_OK && m->row_path == 1) ensure_scatter_plan(m);
@@ -401,7 +429,7 @@ int sb200_matrix_dims(const sb200_matrix* m, int32_t* nrow, int32_t* ncol, int64
 }
 
 int sb200_matrix_refresh_values(sb200_matrix* m, const double* x) {
-  ENTER(m);
+  ENTER_COLS(m);
   if (m->nnz == 0) return SB200_OK;
   if (!x) return fail(SB200_E_INVALID, "x is NULL");
   drop_row_companion(m);  // its values are the old ones; the call count starts over
@@ -417,7 +445,7 @@ int sb200_matrix_refresh_values(sb200_matrix* m, const double* x) {
 }
 
 int sb200_matrix_set_stream(sb200_matrix* m, void* cuda_stream) {
-  ENTER(m);
+  ENTER_COLS(m);
   SB_CUDA(cudaStreamSynchronize(m->stream));
   if (m->owns_stream && m->stream) cudaStreamDestroy(m->stream);
   m->stream = static_cast<cudaStream_t>(cuda_stream);
@@ -426,13 +454,18 @@ int sb200_matrix_set_stream(sb200_matrix* m, void* cuda_stream) {
 }
 
 int sb200_matrix_sync(sb200_matrix* m) {
-  ENTER(m);
+  ENTER_COLS(m);
   SB_CUDA(cudaStreamSynchronize(m->stream));
   return SB200_OK;
 }
 
 int sb200_matrix_device_arrays(const sb200_matrix* m, const int32_t** d_i, const int32_t** d_p, const double** d_x) {
   SB_TRY(check_handle(m));
+  if (d_i && m->lazy_i) {  // the caller is about to read the row indices on the device
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(SB200_E_CUDA, "cudaSetDevice failed");
+    SB_TRY(ensure_rows(const_cast<sb200_matrix*>(m)));
+  }
   if (d_i) *d_i = m->d_i;
   if (d_p) *d_p = m->d_p;
   if (d_x) *d_x = m->d_x;
@@ -441,7 +474,7 @@ int sb200_matrix_device_arrays(const sb200_matrix* m, const int32_t** d_i, const
 
 // ---- device-buffer form ---------------------------------------------------------------------------------
 int sb200_col_sums_dev(sb200_matrix* m, double divisor, double* d_out) {
-  ENTER(m);
+  ENTER_COLS(m);
   if (m->ncol > 0 && !d_out) return fail(SB200_E_INVALID, "d_out is NULL");
   return launch_sweep(m, SWEEP_COLSUM, nullptr, divisor, d_out);
 }
@@ -461,7 +494,7 @@ int sb200_spmv_t_dev(sb200_matrix* m, const double* d_v, double* d_y) {
   return launch_sweep(m, SWEEP_SPMV_T, d_v, 0.0, d_y);
 }
 int sb200_vec_div_dev(sb200_matrix* m, double* d, int64_t n, double divisor) {
-  ENTER(m);
+  ENTER_COLS(m);
   return launch_vec_div(m->stream, d, n, divisor);
 }
 
@@ -518,7 +551,7 @@ static int run_to_host(sb200_matrix* m, SweepMode mode, const double* v_host, in
 }
 
 int sb200_col_sums(sb200_matrix* m, double* out) {
-  ENTER(m);
+  ENTER_COLS(m);
   return run_to_host(m, SWEEP_COLSUM, nullptr, 0, 0.0, out, m->ncol);
 }
 int sb200_row_sums(sb200_matrix* m, double* out) {
@@ -526,7 +559,7 @@ int sb200_row_sums(sb200_matrix* m, double* out) {
   return run_to_host(m, SWEEP_ROWSUM, nullptr, 0, 0.0, out, m->nrow);
 }
 int sb200_col_means(sb200_matrix* m, double* out) {
-  ENTER(m);
+  ENTER_COLS(m);
   // RcppSparse.h:148: sums[i] / Dim[0]; Dim[0] == 0 gives 0/0 = NaN there and here
   if (m->nrow == 0) {
     for (int32_t c = 0; c < m->ncol; ++c) out[c] = 0.0 / static_cast<double>(m->nrow);
@@ -708,7 +741,7 @@ int sb200_matrix_band_companion(sb200_matrix* m, int which, int action) {
 }
 
 int sb200_matrix_layouts(sb200_matrix* m, int* mask) {
-  ENTER(m);
+  ENTER_COLS(m);
   if (!mask) return fail(SB200_E_INVALID, "mask is NULL");
   *mask = (m->rows_state == 1 ? 1 : 0) | (m->bmc_state == 1 ? 2 : 0) |
           ((m->rows_state == 1 && m->rows && m->rows->bmc_state == 1) ? 4 : 0) | ((m->plan_transpose || m->plan_split) ? 8 : 0);
@@ -716,7 +749,7 @@ int sb200_matrix_layouts(sb200_matrix* m, int* mask) {
 }
 
 int sb200_matrix_layout_bytes(sb200_matrix* m, int64_t* bytes) {
-  ENTER(m);
+  ENTER_COLS(m);
   if (!bytes) return fail(SB200_E_INVALID, "bytes is NULL");
   int64_t total = band_companion_bytes(m);
   if (m->rows_state == 1 && m->rows) {

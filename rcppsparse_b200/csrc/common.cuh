@@ -102,6 +102,9 @@ struct sb200_matrix {
   int spmv_t_calls;   // A^T v calls served by the L2-gather sweep since the last (re)build decision
   sb200::BandPlan* plan_transpose;  // band plan of the transpose, kept between calls (structure only)
   sb200::SplitPlan* plan_split;     // same for the two-split transpose of tall matrices (transpose_split.cu)
+  // SB200_LAZY_ROWS: the caller's row indices, still on the host; d_i is allocated but not filled until ensure_rows()
+  const int32_t* lazy_i;
+  bool lazy_validate;
 };
 
 namespace sb200 {
@@ -133,7 +136,9 @@ int launch_sweep(sb200_matrix* m, SweepMode mode, const double* d_v, double divi
 int launch_vec_div(cudaStream_t s, double* d, int64_t n, double divisor);
 
 // validate.cu
-int validate_structure(sb200_matrix* m);
+int validate_structure(sb200_matrix* m, bool rows = true);  // p always; i (range, ascending inside a column) when rows
+int validate_rows(sb200_matrix* m);                         // i alone, once p is known to be sound
+int ensure_rows(sb200_matrix* m);                           // capi.cu: upload and check a lazily kept `i` (SB200_LAZY_ROWS)
 
 // scan.cu — exclusive prefix sum of u32 counts into int32 offsets (out has n+1 entries);
 // d_total (optional) receives the 64-bit grand total.  ws must hold scan_workspace_bytes(n).

@@ -77,6 +77,7 @@ int sb200_col_sums_in_rows(sb200_matrix* m, const int32_t* rows, int64_t n, int 
   SB_TRY(check_handle(m));
   DeviceGuard guard(m->device);
   if (!guard.ok) return fail(SB200_E_CUDA, "cudaSetDevice failed");
+  SB_TRY(ensure_rows(m));  // a mirror created with SB200_LAZY_ROWS gets its row indices now
   if (n < 0 || (n > 0 && !rows)) return fail(SB200_E_INVALID, "sb200_col_sums_in_rows: bad index set");
   if (m->ncol > 0 && !out) return fail(SB200_E_INVALID, "output buffer is NULL");
   cudaStream_t st = m->stream;
@@ -110,6 +111,7 @@ int sb200_gather_block(sb200_matrix* m, const int32_t* rows, int64_t nr, const i
   SB_TRY(check_handle(m));
   DeviceGuard guard(m->device);
   if (!guard.ok) return fail(SB200_E_CUDA, "cudaSetDevice failed");
+  SB_TRY(ensure_rows(m));  // a mirror created with SB200_LAZY_ROWS gets its row indices now
   if (!rows) nr = m->nrow;
   if (!cols) nc = m->ncol;
   if (nr < 0 || nc < 0) return fail(SB200_E_INVALID, "sb200_gather_block: negative size");

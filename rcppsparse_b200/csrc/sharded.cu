@@ -259,7 +259,7 @@ int sb200_sharded_create(const int32_t* i, const int32_t* p, const double* x, in
         errs[k] = "p is not monotone";
         return;
       }
-      rcs[k] = sb200_matrix_create(i + k0, pk.data(), x + k0, nrow, static_cast<int32_t>(c1 - c0), k1 - k0, s->devices[k], flags,
+      rcs[k] = sb200_matrix_create(i + k0, pk.data(), x + k0, nrow, static_cast<int32_t>(c1 - c0), k1 - k0, s->devices[k], flags & ~SB200_LAZY_ROWS,
                                    &s->blocks[k]);
       if (rcs[k] != SB200_OK) errs[k] = sb200_last_error();
     });

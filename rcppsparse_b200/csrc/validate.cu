@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+
 #include "common.cuh"
 
 namespace sb200 {
@@ -63,8 +65,39 @@ __global__ void validate_i_kernel(const int32_t* __restrict__ i, const int32_t* 
 
 }  // namespace
 
-int validate_structure(sb200_matrix* m) {
+namespace {
+
+int structure_error(unsigned h_err) {
+  std::string msg = "dgCMatrix structure invalid:";
+  if (h_err & BAD_P0) msg += " p[0] != 0;";
+  if (h_err & BAD_PN) msg += " p[ncol] != nnz;";
+  if (h_err & BAD_P_ORDER) msg += " p not non-decreasing within [0, nnz];";
+  if (h_err & BAD_I_RANGE) msg += " row index outside [0, nrow) (reference: Rcpp::index_out_of_bounds at RcppSparse.h:142);";
+  if (h_err & BAD_I_ORDER) msg += " row indices not strictly ascending inside a column;";
+  return fail(SB200_E_STRUCTURE, msg);
+}
+
+}  // namespace
+
+// i alone; p has been checked (binary searches over it are meaningful)
+int validate_rows(sb200_matrix* m) {
+  if (m->nnz <= 0) return SB200_OK;
   unsigned* d_err = static_cast<unsigned*>(m->d_ws);  // first word of the workspace; re-zeroed below
+  SB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned), m->stream));
+  int64_t blocks = (m->nnz + 255) / 256;
+  if (blocks > m->sm_count * 16) blocks = m->sm_count * 16;
+  validate_i_kernel<<<static_cast<unsigned>(blocks), 256, 0, m->stream>>>(m->d_i, m->d_p, m->ncol, m->nnz, m->nrow, d_err);
+  count_launch();
+  SB_CUDA(cudaGetLastError());
+  unsigned h_err = 0;
+  SB_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, m->stream));
+  SB_CUDA(cudaStreamSynchronize(m->stream));
+  SB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned), m->stream));  // the sweep's ticket lives here
+  return h_err ? structure_error(h_err) : SB200_OK;
+}
+
+int validate_structure(sb200_matrix* m, bool rows) {
+  unsigned* d_err = static_cast<unsigned*>(m->d_ws);
   SB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned), m->stream));
   {
     int64_t blocks = (static_cast<int64_t>(m->ncol) + 1 + 255) / 256;
@@ -76,28 +109,9 @@ int validate_structure(sb200_matrix* m) {
   unsigned h_err = 0;
   SB_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, m->stream));
   SB_CUDA(cudaStreamSynchronize(m->stream));
-  if (h_err == 0 && m->nnz > 0) {
-    // p is sound, so binary searches over it are meaningful
-    int64_t blocks = (m->nnz + 255) / 256;
-    if (blocks > m->sm_count * 16) blocks = m->sm_count * 16;
-    validate_i_kernel<<<static_cast<unsigned>(blocks), 256, 0, m->stream>>>(m->d_i, m->d_p, m->ncol, m->nnz, m->nrow,
-                                                                          d_err);
-    count_launch();
-    SB_CUDA(cudaGetLastError());
-    SB_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, m->stream));
-    SB_CUDA(cudaStreamSynchronize(m->stream));
-  }
-  SB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned), m->stream));  // the sweep's ticket lives here
-  if (h_err != 0) {
-    std::string msg = "dgCMatrix structure invalid:";
-    if (h_err & BAD_P0) msg += " p[0] != 0;";
-    if (h_err & BAD_PN) msg += " p[ncol] != nnz;";
-    if (h_err & BAD_P_ORDER) msg += " p not non-decreasing within [0, nnz];";
-    if (h_err & BAD_I_RANGE) msg += " row index outside [0, nrow) (reference: Rcpp::index_out_of_bounds at RcppSparse.h:142);";
-    if (h_err & BAD_I_ORDER) msg += " row indices not strictly ascending inside a column;";
-    return fail(SB200_E_STRUCTURE, msg);
-  }
-  return SB200_OK;
+  SB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned), m->stream));
+  if (h_err != 0) return structure_error(h_err);
+  return rows ? validate_rows(m) : SB200_OK;
 }
 
 }  // namespace sb200

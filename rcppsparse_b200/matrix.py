@@ -52,8 +52,10 @@ class DeviceMatrix:
     # ---- construction ---------------------------------------------------------------------------
     @classmethod
     def from_host(cls, i, p, x, nrow: int, ncol: int, device: int = 0, pin: bool = False,
-                  validate: bool = True) -> "DeviceMatrix":
-        """Upload host i/p/x (numpy or pinned torch CPU tensors). reference: Exporter::get(), RcppSparse.h:417-419."""
+                  validate: bool = True, lazy_rows: bool = False) -> "DeviceMatrix":
+        """Upload host i/p/x (numpy or pinned torch CPU tensors). reference: Exporter::get(), RcppSparse.h:417-419.
+        lazy_rows (SB200_LAZY_ROWS): `i` goes up only when an op reads it — colSums / colMeans never do (the reference's
+        loops do not either, RcppSparse.h:133-135); the array is kept alive by the object and must not change meanwhile."""
         nnz = int(x.shape[0])
         if isinstance(i, np.ndarray):
             if i.dtype != np.int32 or p.dtype != np.int32 or x.dtype != np.float64:
@@ -62,10 +64,13 @@ class DeviceMatrix:
                 raise ValueError("slot arrays must be contiguous")
         if int(p.shape[0]) != ncol + 1:
             raise ValueError("p must have ncol + 1 entries")
-        flags = (_lib.PIN_HOST if pin else 0) | (0 if validate else _lib.NO_VALIDATE)
+        flags = (_lib.PIN_HOST if pin else 0) | (0 if validate else _lib.NO_VALIDATE) | (_lib.LAZY_ROWS if lazy_rows else 0)
         out = C.c_void_p()
         check(_lib.lib().sb200_matrix_create(_ptr(i), _ptr(p), _ptr(x), nrow, ncol, nnz, device, flags, C.byref(out)))
-        return cls(out.value)
+        obj = cls(out.value)
+        if lazy_rows:
+            obj._lazy_i = i  # the library reads it on the first row-indexed call
+        return obj
 
     @classmethod
     def adopt(cls, d_i, d_p, d_x, nrow: int, ncol: int, device: int = 0, validate: bool = False) -> "DeviceMatrix":
@@ -484,7 +489,8 @@ class Matrix:
             return self._sharded
         if self._dev is None:
             i, p, x = self._slots()
-            self._dev = DeviceMatrix.from_host(i, p, x, self.rows(), self.cols(), self._device, self._pin)
+            self._dev = DeviceMatrix.from_host(i, p, x, self.rows(), self.cols(), self._device, self._pin,
+                                               lazy_rows=not self._resident)  # a per-call mirror: the slots outlive it
         return self._dev
 
     def _call(self, multi: bool, fn):
