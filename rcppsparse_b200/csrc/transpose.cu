@@ -57,6 +57,7 @@ struct PlaceArgs {
   int kcols;     // columns per thread and chunk (1..PL_KMAX)
   unsigned int* unit_counter;  // zeroed before the launch
   int prefetch;  // pull the next chunk's runs towards L2 while this one is placed
+  int carry;     // bitmap-rank kernel: only full rounds of E entries; what a window leaves over opens the next window
 };
 
 template <int THREADS, int E>
@@ -303,7 +304,7 @@ struct PlGeomB {
 };
 
 template <int THREADS, int E>
-__global__ void __launch_bounds__(THREADS, (E <= 2048) ? 3 : 2) transpose_bitrank_kernel(const PlaceArgs a) {
+__global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : (E <= 1024 ? 4 : (E <= 2048 ? 3 : 2))) transpose_bitrank_kernel(const PlaceArgs a) {
   constexpr int W = THREADS / 32;
   constexpr int EPT = E / THREADS;  // flat slots per thread and round
   static_assert(EPT * THREADS == E, "E must be a multiple of the block size");
@@ -311,6 +312,9 @@ __global__ void __launch_bounds__(THREADS, (E <= 2048) ? 3 : 2) transpose_bitran
   __shared__ uint32_t wsum[2][W];
   __shared__ uint32_t wscan[W];
   __shared__ int s_unit;
+  __shared__ int64_t s_next_c[2];  // carry: first column of the next window (two copies, like wsum: a window without
+  __shared__ int32_t s_next_k[2];  // entries has no barrier after these are read), and the first entry of that column's
+                                   // run that is still to be placed (-1: the whole run)
 
   const BandView& bv = a.bv;
   const int MR = a.max_rows, K = a.kcols;
@@ -356,7 +360,12 @@ __global__ void __launch_bounds__(THREADS, (E <= 2048) ? 3 : 2) transpose_bitran
         ne[kk] = band_start(bv, b + 1, c);
       }
     }
-    for (int64_t cbase = c_lo; cbase < c_hi; cbase += CC, ++chunk_no) {
+    // A window is the next CC columns.  Without carry every window is placed whole, E entries a round, and the last
+    // round of a window is as full as it happens to be (C3: 62 % on average, and a round costs the same whatever its
+    // fill).  With carry a window that is not the unit's last one is placed in FULL rounds only: the columns it leaves
+    // over — the first of them possibly from the middle of its run, rows are unique inside a column so a run may be cut
+    // anywhere — open the next window.
+    for (int64_t cbase = c_lo; cbase < c_hi; ++chunk_no) {
       int32_t rs[PB_KMAX], rl[PB_KMAX];
       uint32_t ex[PB_KMAX];
       uint32_t wtot = 0;
@@ -373,17 +382,12 @@ __global__ void __launch_bounds__(THREADS, (E <= 2048) ? 3 : 2) transpose_bitran
         ex[kk] = wtot + incl - static_cast<uint32_t>(rl[kk]);
         wtot += __shfl_sync(0xffffffffu, incl, 31);
       }
-#pragma unroll
-      for (int kk = 0; kk < PB_KMAX; ++kk) {  // next chunk's descriptors
-        ns[kk] = ne[kk] = 0;
-        const int64_t c = cbase + CC + (warp * K + kk) * 32 + lane;
-        if (kk < K && c < c_hi) {
-          ns[kk] = band_start(bv, b, c);
-          ne[kk] = band_start(bv, b + 1, c);
-        }
-      }
       const int par = chunk_no & 1;
       if (lane == 0) wsum[par][warp] = wtot;
+      if (tid == 0) {
+        s_next_c[par] = cbase + CC;
+        s_next_k[par] = -1;
+      }
       __syncthreads();
       uint32_t woff = 0, total = 0;
 #pragma unroll
@@ -392,9 +396,35 @@ __global__ void __launch_bounds__(THREADS, (E <= 2048) ? 3 : 2) transpose_bitran
         if (w < warp) woff += v;
         total += v;
       }
+      const bool last_window = cbase + CC >= c_hi;
+      const uint32_t limit = (a.carry && !last_window && total >= static_cast<uint32_t>(E)) ? (total / E) * E : total;
+      if (limit < total) {  // the run that holds flat slot `limit` opens the next window
+#pragma unroll
+        for (int kk = 0; kk < PB_KMAX; ++kk) {
+          const uint32_t q0 = woff + ex[kk];
+          if (kk < K && rl[kk] > 0 && q0 <= limit && limit < q0 + static_cast<uint32_t>(rl[kk])) {
+            s_next_c[par] = cbase + (warp * K + kk) * 32 + lane;
+            s_next_k[par] = rs[kk] + static_cast<int32_t>(limit - q0);
+          }
+        }
+      }
+      __syncthreads();
+      const int64_t next_c = s_next_c[par];
+      const int32_t next_k = s_next_k[par];
+#pragma unroll
+      for (int kk = 0; kk < PB_KMAX; ++kk) {  // next window's descriptors
+        ns[kk] = ne[kk] = 0;
+        const int ci = (warp * K + kk) * 32 + lane;
+        const int64_t c = next_c + ci;
+        if (kk < K && c < c_hi) {
+          ns[kk] = (ci == 0 && next_k >= 0) ? next_k : band_start(bv, b, c);
+          ne[kk] = band_start(bv, b + 1, c);
+        }
+      }
       const int32_t col0 = static_cast<int32_t>(cbase);
-      for (uint32_t lo = 0; lo < total; lo += E) {
-        const uint32_t hi = (lo + E < total) ? lo + E : total;
+      cbase = next_c;
+      for (uint32_t lo = 0; lo < limit; lo += E) {
+        const uint32_t hi = (lo + E < limit) ? lo + E : limit;
         const uint32_t n = hi - lo;
         // ---- clear the bitmap of the rows in use; owner expansion of the flat slots [lo, hi) -----------------------
         for (int e = tid; e < R * WW; e += THREADS) bm[e] = 0u;
@@ -530,6 +560,10 @@ int launch_place(sb200_matrix* m, const BandPlan* bp, int32_t* d_i_out, double* 
   if (bitmap && K > 2) K = 2;  // the bitmap has THREADS * K bits per row
   a.kcols = K;
   a.prefetch = getenv("SB200_TRANSPOSE_PF") ? 1 : 0;  // measured: the L2 prefetch of the next chunk's runs costs more than it hides
+  {
+    const char* e = getenv("SB200_TRANSPOSE_CARRY");
+    a.carry = (e && atoi(e) == 0) ? 0 : 1;
+  }
   // the unit counter lives in the handle's workspace, behind the lockstep counters
   a.unit_counter = reinterpret_cast<unsigned int*>(static_cast<unsigned char*>(m->d_ws) + 16 + 4 * 1024 + 8 * 1024 + 2048);
   SB_CUDA(cudaMemsetAsync(a.unit_counter, 0, sizeof(unsigned int), m->stream));
@@ -658,7 +692,19 @@ int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double
       rc = launch_place<512, 3072>(m, bp, d_i_out, d_x_out);
     else if (cfg && !strcmp(cfg, "256x4096"))
       rc = launch_place<256, 4096>(m, bp, d_i_out, d_x_out);
-    else  // measured at C3 (profiles/r02): 256x2048 (3 CTAs/SM) 26.5-27.8 ms, 256x4096 (2) 28.3-29.1, 128x2048 (4) 31.1, 512x3072 29.4
+    else if (cfg && !strcmp(cfg, "256x1024"))
+      rc = launch_place<256, 1024>(m, bp, d_i_out, d_x_out);
+    else if (cfg && !strcmp(cfg, "512x2048"))
+      rc = launch_place<512, 2048>(m, bp, d_i_out, d_x_out);
+    else if (cfg && !strcmp(cfg, "256x2048"))
+      rc = launch_place<256, 2048>(m, bp, d_i_out, d_x_out);
+    // measured at C3 (profiles/r02), match.any ranks: 256x2048 (3 CTAs/SM) 26.5-27.8 ms, 256x4096 (2) 28.3-29.1, 128x2048 (4)
+    // 31.1, 512x3072 29.4; bitmap ranks with carried windows: 256x2048 23.4-23.5, 256x1024 (4 CTAs/SM) 22.0, 512x2048 (2 CTAs
+    // of 16 warps) 27.3.  The kernel waits on its gathers (ncu: long_scoreboard 4.6 warps per issue, 24 warps per SM): a
+    // fourth CTA per SM is worth more than longer rounds.  Small matrices keep the geometry their crossover was measured with.
+    else if (!cfg && m->nnz >= 8000000)
+      rc = launch_place<256, 1024>(m, bp, d_i_out, d_x_out);
+    else
       rc = launch_place<256, 2048>(m, bp, d_i_out, d_x_out);
   } else {
     rc = launch_transpose_banded(m, bp, d_i_out, d_x_out);

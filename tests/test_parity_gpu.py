@@ -140,13 +140,16 @@ def test_synth_transpose_bit_exact(synth_case, checker):
 
 
 @pytest.mark.parametrize("rank", ["bitmap", "match"])
-@pytest.mark.parametrize("cfg", ["256x2048:1", "256x2048:3", "256x4096:4", "512x3072:2"])
+@pytest.mark.parametrize("cfg", ["256x2048:1", "256x2048:3", "256x4096:4", "512x3072:2", "256x1024:1", "256x1024:2", "512x2048:1",
+                                 "256x1024:1:nocarry", "256x2048:2:nocarry"])
 def test_transpose_chunk_sort_placement_on_every_shape(synth_case, cfg, rank, monkeypatch, checker):
     """The chunk-sorting placement kernel (transpose.cu) forced on every synthetic shape — also the tall ones the
     library would give to the banded two-pass kernel — in both block geometries and with 1, 2 and 4 columns per
     thread and chunk: bit-exact whatever the geometry."""
     name, spec, i, p, x = synth_case
-    geom, kcols = cfg.split(":")
+    geom, kcols = cfg.split(":")[:2]
+    # bitmap ranks place a window in full rounds and carry the rest into the next window; nocarry = whole windows
+    monkeypatch.setenv("SB200_TRANSPOSE_CARRY", "0" if cfg.endswith(":nocarry") else "1")
     monkeypatch.setenv("SB200_TRANSPOSE_PATH", "place")
     monkeypatch.setenv("SB200_TRANSPOSE_RANK", rank)  # bitmap ranks (default) or per-warp counters + match.any
     monkeypatch.setenv("SB200_TRANSPOSE_CFG", geom)
