@@ -303,8 +303,10 @@ struct PlGeomB {
   }
 };
 
-template <int THREADS, int E>
-__global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : (E <= 1024 ? 4 : (E <= 2048 ? 3 : 2))) transpose_bitrank_kernel(const PlaceArgs a) {
+// KC = columns per thread and window (1 or 2), a template argument so that the bitmap's row stride (WW words) and the
+// per-column loops are compile-time (ncu: the index arithmetic around the bitmap was 22 of 240 thread instructions per entry)
+template <int THREADS, int E, int KC>
+__global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : (E <= 512 ? 6 : (E <= 1024 ? 4 : (E <= 2048 ? 3 : 2)))) transpose_bitrank_kernel(const PlaceArgs a) {
   constexpr int W = THREADS / 32;
   constexpr int EPT = E / THREADS;  // flat slots per thread and round
   static_assert(EPT * THREADS == E, "E must be a multiple of the block size");
@@ -317,8 +319,9 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : (E <= 1024 ? 4 :
                                    // run that is still to be placed (-1: the whole run)
 
   const BandView& bv = a.bv;
-  const int MR = a.max_rows, K = a.kcols;
-  const int WW = (THREADS * K) / 32;  // bitmap words per row = columns per chunk / 32
+  const int MR = a.max_rows;
+  constexpr int K = KC;
+  constexpr int WW = (THREADS * K) / 32;  // bitmap words per row = columns per chunk / 32
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   double* img_x = reinterpret_cast<double*>(psm);                // [E] the chunk's output image: values,
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : (E <= 1024 ? 4 :
   uint16_t* flat_c = img_r + E;                                  // [E] column inside the chunk
 
   const int units = bv.nb * bv.S;
-  const int CC = THREADS * K;
+  constexpr int CC = THREADS * K;
   const int IT = (MR + THREADS - 1) / THREADS;
   int chunk_no = 0;
 
@@ -350,9 +353,9 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : (E <= 1024 ? 4 :
     if (R <= 0 || c_lo >= c_hi) continue;
     for (int r = tid; r < R; r += THREADS) cursor[r] = static_cast<uint32_t>(a.off[static_cast<int64_t>(row0 + r) * bv.S + h]);
 
-    int32_t ns[PB_KMAX], ne[PB_KMAX];
+    int32_t ns[KC], ne[KC];
 #pragma unroll
-    for (int kk = 0; kk < PB_KMAX; ++kk) {
+    for (int kk = 0; kk < KC; ++kk) {
       ns[kk] = ne[kk] = 0;
       const int64_t c = static_cast<int64_t>(c_lo) + (warp * K + kk) * 32 + lane;
       if (kk < K && c < c_hi) {
@@ -366,11 +369,11 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : (E <= 1024 ? 4 :
     // over — the first of them possibly from the middle of its run, rows are unique inside a column so a run may be cut
     // anywhere — open the next window.
     for (int64_t cbase = c_lo; cbase < c_hi; ++chunk_no) {
-      int32_t rs[PB_KMAX], rl[PB_KMAX];
-      uint32_t ex[PB_KMAX];
+      int32_t rs[KC], rl[KC];
+      uint32_t ex[KC];
       uint32_t wtot = 0;
 #pragma unroll
-      for (int kk = 0; kk < PB_KMAX; ++kk) {
+      for (int kk = 0; kk < KC; ++kk) {
         rs[kk] = ns[kk];
         rl[kk] = ne[kk] - ns[kk];
         uint32_t incl = static_cast<uint32_t>(rl[kk]);
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : (E <= 1024 ? 4 :
       const uint32_t limit = (a.carry && !last_window && total >= static_cast<uint32_t>(E)) ? (total / E) * E : total;
       if (limit < total) {  // the run that holds flat slot `limit` opens the next window
 #pragma unroll
-        for (int kk = 0; kk < PB_KMAX; ++kk) {
+        for (int kk = 0; kk < KC; ++kk) {
           const uint32_t q0 = woff + ex[kk];
           if (kk < K && rl[kk] > 0 && q0 <= limit && limit < q0 + static_cast<uint32_t>(rl[kk])) {
             s_next_c[par] = cbase + (warp * K + kk) * 32 + lane;
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : (E <= 1024 ? 4 :
       const int64_t next_c = s_next_c[par];
       const int32_t next_k = s_next_k[par];
 #pragma unroll
-      for (int kk = 0; kk < PB_KMAX; ++kk) {  // next window's descriptors
+      for (int kk = 0; kk < KC; ++kk) {  // next window's descriptors
         ns[kk] = ne[kk] = 0;
         const int ci = (warp * K + kk) * 32 + lane;
         const int64_t c = next_c + ci;
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : (E <= 1024 ? 4 :
         // ---- clear the bitmap of the rows in use; owner expansion of the flat slots [lo, hi) -----------------------
         for (int e = tid; e < R * WW; e += THREADS) bm[e] = 0u;
 #pragma unroll
-        for (int kk = 0; kk < PB_KMAX; ++kk) {
+        for (int kk = 0; kk < KC; ++kk) {
           if (kk < K && rl[kk] > 0) {
             const uint32_t q0 = woff + ex[kk];
             const uint32_t q1 = q0 + static_cast<uint32_t>(rl[kk]);
@@ -474,6 +477,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : (E <= 1024 ? 4 :
           const int r = tid * IT + it;
           if (r < R) {
             uint32_t run = 0;
+#pragma unroll
             for (int w = 0; w < WW; ++w) {
               pre[r * WW + w] = static_cast<uint16_t>(run);
               run += __popc(bm[r * WW + w]);
@@ -575,7 +579,7 @@ int launch_place(sb200_matrix* m, const BandPlan* bp, int32_t* d_i_out, double* 
   int grid = m->sm_count * per_sm;
   if (grid > bp->nb * bp->S) grid = bp->nb * bp->S;
   if (bitmap) {
-    auto kern = transpose_bitrank_kernel<THREADS, E>;
+    auto kern = K == 1 ? transpose_bitrank_kernel<THREADS, E, 1> : transpose_bitrank_kernel<THREADS, E, 2>;
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<grid, THREADS, smem, m->stream>>>(a);
   } else {
@@ -694,6 +698,8 @@ int transpose_device(sb200_matrix* m, int32_t* d_p_out, int32_t* d_i_out, double
       rc = launch_place<256, 4096>(m, bp, d_i_out, d_x_out);
     else if (cfg && !strcmp(cfg, "256x1024"))
       rc = launch_place<256, 1024>(m, bp, d_i_out, d_x_out);
+    else if (cfg && !strcmp(cfg, "256x512"))
+      rc = launch_place<256, 512>(m, bp, d_i_out, d_x_out);
     else if (cfg && !strcmp(cfg, "512x2048"))
       rc = launch_place<512, 2048>(m, bp, d_i_out, d_x_out);
     else if (cfg && !strcmp(cfg, "256x2048"))
