@@ -31,6 +31,18 @@ def test_header_declares_what_the_binding_binds():
     assert declared_symbols() == sorted(_lib.SYMBOLS)
 
 
+def test_status_codes_and_create_flags_agree_with_the_header():
+    """The ctypes binding repeats the header's constants: status codes and the flags of sb200_matrix_create."""
+    from rcppsparse_b200 import _lib
+
+    src = open(HEADER).read()
+    consts = {k: v for k, v in re.findall(r"#define\s+SB200_([A-Z_]+)\s+\(?(-?\d+)u?\)?", src)}
+    for name in ("E_INVALID", "E_CUDA", "E_NOMEM", "E_STRUCTURE", "E_NODEVICE", "E_UNSUPPORTED",
+                 "PIN_HOST", "NO_VALIDATE", "NO_ROW_PLAN", "LAZY_ROWS"):
+        assert name in consts, name
+        assert int(consts[name]) == getattr(_lib, name), name
+
+
 def test_library_exports_every_declared_symbol(built_lib):
     out = subprocess.run(["nm", "-D", "--defined-only", built_lib], capture_output=True, text=True, check=True).stdout
     exported = set(re.findall(r"\bT (sb200_[a-z0-9_]+)", out))
