@@ -76,8 +76,8 @@ void configure(int dev) {
     uint64_t keep = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
-  size_t free_b = 0, total_b = 0;
-  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) dc.limit = total_b / 3;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) dc.limit = prop.totalGlobalMem / 3;
   if (const char* e = getenv("SB200_CACHE_MB")) dc.limit = static_cast<size_t>(atoll(e)) << 20;
   cudaGetLastError();
 }
@@ -183,8 +183,14 @@ void pool_free(void* ptr, cudaStream_t s) {
   Block b = it->second;
   cache().live.erase(it);
   DeviceCache& dc = cache().dev[b.device];
-  if (cudaEventRecord(b.ev, s) != cudaSuccess || b.cap > dc.limit) {
+  if (cudaEventRecord(b.ev, s) != cudaSuccess) {  // a stream that is gone: nothing can be ordered after it any more
     cudaGetLastError();
+    cudaEventDestroy(b.ev);
+    cudaFree(b.ptr);  // synchronising free, valid for pool memory
+    cudaGetLastError();
+    return;
+  }
+  if (b.cap > dc.limit) {  // larger than the whole cache (or the cache is off): straight back to the driver pool
     cudaEventDestroy(b.ev);
     b.ev = nullptr;
     release_to_driver(b, s);
